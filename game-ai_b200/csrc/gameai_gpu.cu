@@ -1,0 +1,525 @@
+// game-ai_b200/csrc/gameai_gpu.cu -- C ABI of libgameai_gpu.so (see include/gameai_gpu.h).
+// Context = one device, one stream, pinned staging + device scratch grown on demand.  No CPU fallback.
+#include "gameai_gpu.h"
+#include "kernels.h"
+#include "gameai/philox.h"
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <mutex>
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+struct Buf {            // grow-only device or pinned-host buffer
+	void* p = nullptr; size_t cap = 0; bool host = false;
+};
+
+// minimal NCCL surface, resolved at run time (dlopen) so the library loads without NCCL installed
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+	void* h = nullptr;
+	int (*GetUniqueId)(void*) = nullptr;
+	int (*CommInitRank)(ncclComm_t*, int, /* ncclUniqueId by value: 128 bytes */ struct Id128, int) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*CommDestroy)(ncclComm_t) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+};
+struct Id128 { char b[128]; };
+
+} // namespace
+
+struct gai_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	cudaDeviceProp prop;
+	char err[512];
+	uint64_t launches = 0;
+	int threads = 256, blocks_per_sm = 4;
+	// scratch
+	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc;
+	Buf h_in, h_in2, h_out, h_out2, h_out3;
+	// async rollout bookkeeping
+	gai_loa_result* pending_out = nullptr; uint32_t pending_n = 0;
+	// nccl
+	NcclApi nccl; ncclComm_t comm = nullptr; int rank = 0, world = 1;
+};
+
+namespace {
+
+int fail(gai_ctx* c, int code, const char* fmt, const char* a = "", const char* b = "")
+{
+	if (c) snprintf(c->err, sizeof c->err, fmt, a, b);
+	else snprintf(g_create_error, sizeof g_create_error, fmt, a, b);
+	return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GAI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+int ensure(gai_ctx* ctx, Buf& b, size_t bytes, bool host)
+{
+	if (bytes <= b.cap) return GAI_OK;
+	size_t cap = bytes + bytes / 4 + 256;
+	if (b.p) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	b.host = host;
+	cudaError_t e = host ? cudaMallocHost(&b.p, cap) : cudaMalloc(&b.p, cap);
+	if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, GAI_ERR_NOMEM, "%s of scratch failed: %s", host ? "cudaMallocHost" : "cudaMalloc", cudaGetErrorString(e)); }
+	b.cap = cap;
+	return GAI_OK;
+}
+#define EN(buf, bytes, host) do { int r_ = ensure(ctx, buf, (bytes), host); if (r_) return r_; } while (0)
+
+void release(Buf& b) { if (b.p) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); } b.p = nullptr; b.cap = 0; }
+
+int check_launch(gai_ctx* ctx, const char* what)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(ctx, GAI_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+	ctx->launches += 1;
+	return GAI_OK;
+}
+#define LAUNCHED(what) do { int r_ = check_launch(ctx, what); if (r_) return r_; } while (0)
+
+int rollout_grid(const gai_ctx* ctx, uint64_t total_items)
+{
+	int blocks = ctx->prop.multiProcessorCount * ctx->blocks_per_sm;      // persistent: a multiple of the SM count
+	const uint64_t need = (total_items + ctx->threads - 1) / ctx->threads;
+	if (need < (uint64_t)blocks) blocks = (int)(need ? need : 1);
+	return blocks;
+}
+
+// enqueue: zero out/stat/counter, rollout kernel.  d_misc layout: [0..1] stats u64, [2] work counter.
+int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl,
+                    uint32_t max_plies, uint64_t key, uint64_t first_id, void* d_out)
+{
+	EN(ctx->d_misc, 64, false);
+	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
+	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
+	const uint64_t total = (uint64_t)n_leaves * ppl;
+	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
+	                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
+	                   ctx->threads, rollout_grid(ctx, total), ctx->stream);
+	LAUNCHED("k_rollout");
+	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+	return GAI_OK;
+}
+
+int fill_stats(gai_ctx* ctx, gai_rollout_stats* stats, bool have_total)
+{
+	if (!stats) return GAI_OK;
+	uint64_t h[2];
+	CU(cudaMemcpy(h, ctx->d_misc.p, sizeof h, cudaMemcpyDeviceToHost));
+	stats->playouts = h[0]; stats->plies = h[1];
+	CU(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
+	stats->total_ms = stats->kernel_ms;
+	if (have_total) CU(cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
+	return GAI_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gai_abi_version(void) { return GAI_ABI_VERSION; }
+
+void gai_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+	const gai::Philox4 r = gai::philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+	for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+}
+
+int gai_create(int device, gai_ctx** out)
+{
+	if (!out) return fail(nullptr, GAI_ERR_INVALID, "gai_create: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(nullptr, GAI_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (device < 0 || device >= count) return fail(nullptr, GAI_ERR_INVALID, "gai_create: device ordinal out of range");
+	gai_ctx* ctx = new gai_ctx();
+	ctx->err[0] = 0;
+	ctx->device = device;
+	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
+		fail(nullptr, GAI_ERR_CUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e)); delete ctx; return GAI_ERR_CUDA;
+	}
+	if (ctx->prop.major != 10) {
+		fail(nullptr, GAI_ERR_NO_DEVICE, "device %s is not sm_100 (kernels are built for sm_100a only)", ctx->prop.name); delete ctx; return GAI_ERR_NO_DEVICE;
+	}
+	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		fail(nullptr, GAI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return GAI_ERR_CUDA;
+	}
+	for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+	*out = ctx;
+	return GAI_OK;
+}
+
+void gai_destroy(gai_ctx* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+	for (Buf* b : { &ctx->d_in, &ctx->d_in2, &ctx->d_out, &ctx->d_out2, &ctx->d_out3, &ctx->d_boards, &ctx->d_stm, &ctx->d_misc,
+	                &ctx->h_in, &ctx->h_in2, &ctx->h_out, &ctx->h_out2, &ctx->h_out3 }) release(*b);
+	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char* gai_last_error(const gai_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int gai_get_device_info(gai_ctx* ctx, gai_device_info* info)
+{
+	if (!ctx || !info) return GAI_ERR_INVALID;
+	memset(info, 0, sizeof *info);
+	info->device = ctx->device;
+	info->sm_count = ctx->prop.multiProcessorCount;
+	info->cc_major = ctx->prop.major; info->cc_minor = ctx->prop.minor;
+	int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+	info->clock_khz = khz;
+	info->total_mem = ctx->prop.totalGlobalMem;
+	strncpy(info->name, ctx->prop.name, sizeof info->name - 1);
+	return GAI_OK;
+}
+
+int gai_sync(gai_ctx* ctx)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (ctx->pending_out) {
+		memcpy(ctx->pending_out, ctx->h_out.p, (size_t)ctx->pending_n * sizeof(gai_loa_result));
+		ctx->pending_out = nullptr; ctx->pending_n = 0;
+	}
+	return GAI_OK;
+}
+
+int gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (threads_per_block) {
+		if (threads_per_block < 32 || threads_per_block > 256 || (threads_per_block & 31)) return fail(ctx, GAI_ERR_INVALID, "threads_per_block must be a multiple of 32 in [32,256]");
+		ctx->threads = threads_per_block;
+	}
+	if (blocks_per_sm) {
+		if (blocks_per_sm < 1 || blocks_per_sm > 32) return fail(ctx, GAI_ERR_INVALID, "blocks_per_sm must be in [1,32]");
+		ctx->blocks_per_sm = blocks_per_sm;
+	}
+	return GAI_OK;
+}
+
+uint64_t gai_launch_count(const gai_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- rules sweep ---------------------------------------------------------------------------------
+int gai_loa_movegen(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8_t* counts, gai_loa_move* moves)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n == 0) return GAI_OK;
+	if (!states || !counts || !moves) return fail(ctx, GAI_ERR_INVALID, "gai_loa_movegen: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * sizeof(gai_loa_state), mb = (size_t)n * GAI_LOA_MAX_MOVES * sizeof(gai_loa_move);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, mb, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->d_out2.p, 0, mb, ctx->stream));
+	launch_loa_movegen(ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->stream);
+	LAUNCHED("k_movegen");
+	CU(cudaMemcpyAsync(counts, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(moves, ctx->d_out2.p, mb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+int gai_loa_apply(gai_ctx* ctx, const gai_loa_state* states, const gai_loa_move* mv, uint32_t n, gai_loa_state* out)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n == 0) return GAI_OK;
+	if (!states || !mv || !out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_apply: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * sizeof(gai_loa_state);
+	EN(ctx->d_in, sb, false); EN(ctx->d_in2, (size_t)n * 2, false); EN(ctx->d_out, sb, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_in2.p, mv, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->stream));
+	launch_loa_apply(ctx->d_in.p, (const uint8_t*)ctx->d_in2.p, n, ctx->d_out.p, ctx->stream);
+	LAUNCHED("k_apply");
+	CU(cudaMemcpyAsync(out, ctx->d_out.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+int gai_loa_terminal(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8_t* terminal, uint8_t* score)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n == 0) return GAI_OK;
+	if (!states || !terminal || !score) return fail(ctx, GAI_ERR_INVALID, "gai_loa_terminal: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * sizeof(gai_loa_state);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 2, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	launch_loa_terminal(ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->stream);
+	LAUNCHED("k_terminal");
+	CU(cudaMemcpyAsync(terminal, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(score, ctx->d_out2.p, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+int gai_loa_successor_hash(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint64_t* hash)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n == 0) return GAI_OK;
+	if (!states || !hash) return fail(ctx, GAI_ERR_INVALID, "gai_loa_successor_hash: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * sizeof(gai_loa_state);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, (size_t)n * 8, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	launch_loa_successor_hash(ctx->d_in.p, n, (uint64_t*)ctx->d_out.p, ctx->stream);
+	LAUNCHED("k_successor_hash");
+	CU(cudaMemcpyAsync(hash, ctx->d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+// ---- rollouts --------------------------------------------------------------------------------------
+int gai_loa_pack_states(const gai_loa_state* states, uint32_t n, void* boards16, uint32_t* stm_bits)
+{
+	if (n && (!states || !boards16 || !stm_bits)) return GAI_ERR_INVALID;
+	uint64_t* b = (uint64_t*)boards16;
+	const uint32_t words = (n + 31u) / 32u;
+	for (uint32_t w = 0; w < words; ++w) {
+		uint32_t bits = 0;
+		const uint32_t lo = w * 32u, hi = lo + 32u < n ? lo + 32u : n;
+		for (uint32_t i = lo; i < hi; ++i) {
+			b[2 * (size_t)i] = states[i].white; b[2 * (size_t)i + 1] = states[i].black;
+			bits |= (uint32_t)(states[i].current_player & 1u) << (i - lo);
+		}
+		stm_bits[w] = bits;
+	}
+	return GAI_OK;
+}
+
+static int rollout_host_enqueue(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+                                uint64_t key, uint64_t first_id)
+{
+	if (!leaves) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: leaves is NULL");
+	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: playouts_per_leaf must be >= 1");
+	if (ctx->pending_out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: a batch is already in flight on this context (call gai_sync)");
+	CU(cudaSetDevice(ctx->device));
+	const size_t bb = (size_t)n_leaves * 16, wb = (size_t)((n_leaves + 31u) / 32u) * 4, rb = (size_t)n_leaves * sizeof(gai_loa_result);
+	EN(ctx->h_in, bb, true); EN(ctx->h_in2, wb, true); EN(ctx->h_out, rb, true);
+	EN(ctx->d_boards, bb, false); EN(ctx->d_stm, wb, false); EN(ctx->d_out, rb, false);
+	// repack the reference's 24-byte GameState records into 16-byte boards + side bits, straight into pinned staging
+	gai_loa_pack_states(leaves, n_leaves, ctx->h_in.p, (uint32_t*)ctx->h_in2.p);
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_boards.p, ctx->h_in.p, bb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_stm.p, ctx->h_in2.p, wb, cudaMemcpyHostToDevice, ctx->stream));
+	int r = enqueue_rollout(ctx, ctx->d_boards.p, (const uint32_t*)ctx->d_stm.p, n_leaves, ppl, max_plies, key, first_id, ctx->d_out.p);
+	if (r) return r;
+	CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+	return GAI_OK;
+}
+
+int gai_loa_rollout_async(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
+                          uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id, gai_loa_result* out)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n_leaves == 0) return GAI_OK;
+	if (!out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_async: out is NULL");
+	int r = rollout_host_enqueue(ctx, leaves, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id);
+	if (r) return r;
+	ctx->pending_out = out; ctx->pending_n = n_leaves;
+	return GAI_OK;
+}
+
+int gai_loa_rollout(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
+                    uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id,
+                    gai_loa_result* out, gai_rollout_stats* stats)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (stats) memset(stats, 0, sizeof *stats);
+	if (n_leaves == 0) return GAI_OK;
+	int r = gai_loa_rollout_async(ctx, leaves, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id, out);
+	if (r) return r;
+	r = gai_sync(ctx);
+	if (r) return r;
+	return fill_stats(ctx, stats, true);
+}
+
+int gai_loa_rollout_device(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves,
+                           uint32_t playouts_per_leaf, uint32_t max_plies, uint64_t philox_key,
+                           uint64_t first_playout_id, void* d_out, gai_rollout_stats* stats)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (stats) memset(stats, 0, sizeof *stats);
+	if (n_leaves == 0) return GAI_OK;
+	if (!d_boards || !d_stm || !d_out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_device: NULL buffer");
+	if (playouts_per_leaf == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_device: playouts_per_leaf must be >= 1");
+	CU(cudaSetDevice(ctx->device));
+	int r = enqueue_rollout(ctx, d_boards, d_stm, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id, d_out);
+	if (r) return r;
+	CU(cudaStreamSynchronize(ctx->stream));
+	return fill_stats(ctx, stats, false);
+}
+
+int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint32_t max_plies,
+                          uint64_t philox_key, uint64_t first_playout_id,
+                          uint8_t* outcome, uint32_t* plies, gai_loa_state* final_states)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n == 0) return GAI_OK;
+	if (!states || !outcome || !plies || !final_states) return fail(ctx, GAI_ERR_INVALID, "gai_loa_playout_trace: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * sizeof(gai_loa_state);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 4, false); EN(ctx->d_out3, sb, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	launch_loa_playout_trace(ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
+	                         (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->stream);
+	LAUNCHED("k_playout_trace");
+	CU(cudaMemcpyAsync(outcome, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(plies, ctx->d_out2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(final_states, ctx->d_out3.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+int gai_loa_gen_reachable(gai_ctx* ctx, uint32_t n, uint64_t key, uint32_t max_k,
+                          void* d_boards, uint32_t* d_stm, gai_loa_state* host_states)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (n == 0) return GAI_OK;
+	if (max_k == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_gen_reachable: max_k must be >= 1");
+	if ((d_boards == nullptr) != (d_stm == nullptr)) return fail(ctx, GAI_ERR_INVALID, "gai_loa_gen_reachable: d_boards and d_stm go together");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * sizeof(gai_loa_state);
+	EN(ctx->d_in2, n, false);
+	if (host_states) EN(ctx->d_out3, sb, false);
+	launch_loa_gen_reachable(n, key, max_k, d_boards, host_states ? ctx->d_out3.p : nullptr, (uint8_t*)ctx->d_in2.p, ctx->stream);
+	LAUNCHED("k_gen_reachable");
+	if (d_stm) { launch_loa_pack_stm((const uint8_t*)ctx->d_in2.p, n, d_stm, ctx->stream); LAUNCHED("k_pack_stm"); }
+	if (host_states) CU(cudaMemcpyAsync(host_states, ctx->d_out3.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+// ---- device memory helpers -------------------------------------------------------------------------
+int gai_dev_alloc(gai_ctx* ctx, uint64_t bytes, void** d_ptr)
+{
+	if (!ctx || !d_ptr) return GAI_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+	if (e != cudaSuccess) return fail(ctx, GAI_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+	return GAI_OK;
+}
+int gai_dev_free(gai_ctx* ctx, void* d_ptr)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaFree(d_ptr));
+	return GAI_OK;
+}
+int gai_memcpy_h2d(gai_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+int gai_memcpy_d2h(gai_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+// ---- NCCL (root parallelism) -----------------------------------------------------------------------
+static int nccl_load(NcclApi& a, char* err, size_t errlen)
+{
+	if (a.h) return GAI_OK;
+	const char* names[] = { "libnccl.so.2", "libnccl.so" };
+	for (const char* nm : names) { a.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (a.h) break; }
+	if (!a.h) { snprintf(err, errlen, "dlopen(libnccl.so.2) failed: %s", dlerror()); return GAI_ERR_NCCL; }
+	a.GetUniqueId = (int (*)(void*))dlsym(a.h, "ncclGetUniqueId");
+	a.CommInitRank = (int (*)(ncclComm_t*, int, Id128, int))dlsym(a.h, "ncclCommInitRank");
+	a.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(a.h, "ncclAllReduce");
+	a.CommDestroy = (int (*)(ncclComm_t))dlsym(a.h, "ncclCommDestroy");
+	a.GetErrorString = (const char* (*)(int))dlsym(a.h, "ncclGetErrorString");
+	a.GroupStart = (int (*)())dlsym(a.h, "ncclGroupStart");
+	a.GroupEnd = (int (*)())dlsym(a.h, "ncclGroupEnd");
+	if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) { snprintf(err, errlen, "libnccl lacks a required symbol"); return GAI_ERR_NCCL; }
+	return GAI_OK;
+}
+#define NC(call) do { int e_ = (call); if (e_ != 0) return fail(ctx, GAI_ERR_NCCL, "%s: %s", #call, ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(e_) : "nccl error"); } while (0)
+
+int gai_comm_unique_id(uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES])
+{
+	static NcclApi api;
+	if (!id) return GAI_ERR_INVALID;
+	int r = nccl_load(api, g_create_error, sizeof g_create_error);
+	if (r) return r;
+	Id128 u; memset(&u, 0, sizeof u);
+	if (api.GetUniqueId(&u) != 0) return fail(nullptr, GAI_ERR_NCCL, "ncclGetUniqueId failed");
+	memcpy(id, &u, sizeof u);
+	return GAI_OK;
+}
+
+int gai_comm_init(gai_ctx* ctx, int rank, int world, const uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES])
+{
+	if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return ctx ? fail(ctx, GAI_ERR_INVALID, "gai_comm_init: bad arguments") : GAI_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int r = nccl_load(ctx->nccl, ctx->err, sizeof ctx->err);
+	if (r) return r;
+	Id128 u; memcpy(&u, id, sizeof u);
+	NC(ctx->nccl.CommInitRank(&ctx->comm, world, u, rank));
+	ctx->rank = rank; ctx->world = world;
+	return GAI_OK;
+}
+
+// ncclDataType_t: ncclUint32 = 3, ncclUint64 = 5, ncclFloat32 = 7 ; ncclRedOp_t: ncclSum = 0 (nccl.h, stable since 2.0)
+int gai_allreduce_root(gai_ctx* ctx, uint32_t* visits, float* values, uint32_t count)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (!ctx->comm) return fail(ctx, GAI_ERR_NCCL, "gai_allreduce_root: communicator not initialised (gai_comm_init)");
+	if (count == 0) return GAI_OK;
+	if (!visits || !values) return fail(ctx, GAI_ERR_INVALID, "gai_allreduce_root: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t vb = (size_t)count * 4, fb = (size_t)count * 8;
+	EN(ctx->d_in, vb + fb, false);
+	char* d = (char*)ctx->d_in.p;
+	CU(cudaMemcpyAsync(d, visits, vb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(d + vb, values, fb, cudaMemcpyHostToDevice, ctx->stream));
+	NC(ctx->nccl.GroupStart());
+	NC(ctx->nccl.AllReduce(d, d, count, 3, 0, ctx->comm, ctx->stream));
+	NC(ctx->nccl.AllReduce(d + vb, d + vb, (size_t)count * 2, 7, 0, ctx->comm, ctx->stream));
+	NC(ctx->nccl.GroupEnd());
+	CU(cudaMemcpyAsync(visits, d, vb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(values, d + vb, fb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+int gai_allreduce_u64(gai_ctx* ctx, uint64_t* v, uint32_t count)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (!ctx->comm) return fail(ctx, GAI_ERR_NCCL, "gai_allreduce_u64: communicator not initialised (gai_comm_init)");
+	if (count == 0) return GAI_OK;
+	if (!v) return fail(ctx, GAI_ERR_INVALID, "gai_allreduce_u64: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	EN(ctx->d_in, (size_t)count * 8, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, v, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+	NC(ctx->nccl.AllReduce(ctx->d_in.p, ctx->d_in.p, count, 5, 0, ctx->comm, ctx->stream));
+	CU(cudaMemcpyAsync(v, ctx->d_in.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return GAI_OK;
+}
+
+} // extern "C"

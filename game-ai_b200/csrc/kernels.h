@@ -1,0 +1,19 @@
+// game-ai_b200/csrc/kernels.h -- launch wrappers shared between the kernel TUs and the C ABI.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define GAI_LOA_MAX_MOVES_K 96u
+
+void launch_loa_movegen(const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, cudaStream_t st);
+void launch_loa_apply(const void* d_states, const uint8_t* d_mv, uint32_t n, void* d_out, cudaStream_t st);
+void launch_loa_terminal(const void* d_states, uint32_t n, uint8_t* d_term, uint8_t* d_score, cudaStream_t st);
+void launch_loa_successor_hash(const void* d_states, uint32_t n, uint64_t* d_hash, cudaStream_t st);
+void launch_loa_rollout(const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+                        uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
+                        int threads, int blocks, cudaStream_t st);
+void launch_loa_playout_trace(const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
+                              uint8_t* d_outcome, uint32_t* d_plies, void* d_final, cudaStream_t st);
+void launch_loa_gen_reachable(uint32_t n, uint64_t key, uint32_t max_k, void* d_boards, void* d_states24, uint8_t* d_side, cudaStream_t st);
+void launch_loa_pack_stm(const uint8_t* d_side, uint32_t n, uint32_t* d_stm, cudaStream_t st);
+void launch_loa_split_states(const void* d_states24, uint32_t n, void* d_boards, uint32_t* d_stm, cudaStream_t st);

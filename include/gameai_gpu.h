@@ -1,0 +1,156 @@
+/* include/gameai_gpu.h -- C ABI of libgameai_gpu.so, the B200 (sm_100a) rollout engine.
+ *
+ * This is the drop-in boundary for the simulation (random playout) phase of the reference
+ * MC::Player (c++/MCTSPlayer/MCTSPlayer.cpp:387-470 selection_playOut) on the Lines-of-Action rules
+ * (c++/LinesOfActionZasady/LinesOfActionZasady.cpp) and, for determinized rollouts, the Pan rules
+ * (c++/GraWPanaZasadyV2/GraWPanaZasadyV2.cpp).  Nothing like it exists in the reference (no FFI, no
+ * GPU code): the entry points below are what a GPU-backed IGamePlayer (GamePlayer.h:12-25) binds to
+ * "launch a batch of leaf states, get per-leaf win counts back".  INTEGRATION.md shows the binding.
+ *
+ * Plain C: opaque handle, pointers + sizes, int error codes (0 = GAI_OK), no C++/torch types.
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ *
+ * Each entry point names the reference interface it replaces (path:line under /root/reference/c++).
+ */
+#ifndef GAMEAI_GPU_H
+#define GAMEAI_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAI_ABI_VERSION 1
+
+enum gai_status {
+	GAI_OK = 0,
+	GAI_ERR_INVALID = 1,     /* bad argument */
+	GAI_ERR_CUDA = 2,        /* CUDA runtime error (gai_last_error has the text) */
+	GAI_ERR_NO_DEVICE = 3,   /* no usable sm_100 device: there is no CPU fallback */
+	GAI_ERR_NCCL = 4,
+	GAI_ERR_NOMEM = 5
+};
+
+typedef struct gai_ctx gai_ctx;
+
+/* LinesOfActionZasady.cpp:38-46 `struct GameState { uint64_t white, black; uint64_t current_player:1; }`
+ * -- 24 bytes, bit i = square (row i/8, col i%8), bit 0 = A1; Whites = 0, Blacks = 1.  Only bit 0 of
+ * current_player is read (the upper 63 bits are indeterminate in the reference, ctor :48-51), so a
+ * reference GameState* array can be passed as is. */
+typedef struct gai_loa_state { uint64_t white, black, current_player; } gai_loa_state;
+
+/* LinesOfActionZasady.cpp:16-19 `struct Move { uint8_t from, to; }` */
+typedef struct gai_loa_move { uint8_t from, to; } gai_loa_move;
+#define GAI_LOA_MAX_MOVES 96            /* LinesOfActionZasady.cpp:226 */
+
+/* Per-leaf playout outcome counts.  Replaces the per-simulation Score()/eval back-up of
+ * MCTSPlayer.cpp:478-510: value[white] = (white_wins + 0.5*(draws+capped)) , likewise black
+ * (LinesOfActionZasady.cpp:420-432 Score: both connected -> 50/50; :382-397 eval at the depth cap -> 50/50). */
+typedef struct gai_loa_result { uint32_t white_wins, black_wins, draws, capped; } gai_loa_result;
+
+typedef struct gai_rollout_stats {
+	uint64_t playouts;      /* playouts finished */
+	uint64_t plies;         /* moves applied over all playouts (passes included) */
+	float    kernel_ms;     /* device time of the rollout kernel(s), CUDA events on the ctx stream */
+	float    total_ms;      /* device time H2D + kernels + D2H (host-buffer entry points) */
+} gai_rollout_stats;
+
+typedef struct gai_device_info {
+	int  device;
+	int  sm_count;
+	int  cc_major, cc_minor;
+	int  clock_khz;          /* cudaDevAttrClockRate (max SM clock) */
+	uint64_t total_mem;
+	char name[64];
+} gai_device_info;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  gai_abi_version(void);
+/* create a context (one CUDA stream, pinned staging, device scratch) on `device`. */
+int  gai_create(int device, gai_ctx** out);
+void gai_destroy(gai_ctx* ctx);
+/* text of the last error on ctx (or of the last gai_create failure when ctx == NULL). */
+const char* gai_last_error(const gai_ctx* ctx);
+int  gai_get_device_info(gai_ctx* ctx, gai_device_info* info);
+int  gai_sync(gai_ctx* ctx);
+/* rollout kernel launch shape: threads per block, blocks per SM (0 = keep default). */
+int  gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm);
+/* number of kernel launches issued through ctx since creation (bench.py's gpu_launches) */
+uint64_t gai_launch_count(const gai_ctx* ctx);
+
+/* ---- LOA rules sweep, HOST buffers (tier-1 parity; config 2) ------------------------------- */
+/* IGameRules::GetPlayerLegalMoves (GameRules.h:30; LinesOfActionZasady.cpp:463-471 -> :167-232):
+ * counts[i] = number of moves of the side to move, moves[i*96 + k] = k-th move in reference order. */
+int gai_loa_movegen(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8_t* counts, gai_loa_move* moves);
+/* IGameRules::ApplyMove (GameRules.h:38; LinesOfActionZasady.cpp:481-489 -> :233-252): out[i] = states[i]
+ * after mv[i] by the side to move; from == to means the noop move (side flips only). */
+int gai_loa_apply(gai_ctx* ctx, const gai_loa_state* states, const gai_loa_move* mv, uint32_t n, gai_loa_state* out);
+/* IGameRules::IsTerminal + Score (GameRules.h:27-28; LinesOfActionZasady.cpp:416-432):
+ * terminal[i] in {0,1}; score[2*i], score[2*i+1] = white, black in {0,50,100}. */
+int gai_loa_terminal(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8_t* terminal, uint8_t* score);
+/* all successors: for state i and k < counts[i], succ[i*96+k] = state after move k (checksummed by tests). */
+int gai_loa_successor_hash(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint64_t* hash);
+
+/* ---- LOA rollouts (the hot path; configs 3, 4) ---------------------------------------------- */
+/* HOST buffers, synchronous.  For leaf i and j < playouts_per_leaf runs the uniformly random playout
+ * with id first_playout_id + i*playouts_per_leaf + j from leaves[i] until terminal or max_plies moves,
+ * choosing move (philox(key,id,ply) * n) >> 32 of the reference-ordered list; out[i] accumulates outcomes.
+ * Replaces the playout part of MC::Player::selection_playOut (MCTSPlayer.cpp:387-470) + the Score/eval
+ * read in backpropagation (:478-493).  stats may be NULL. */
+int gai_loa_rollout(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
+                    uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id,
+                    gai_loa_result* out, gai_rollout_stats* stats);
+/* Asynchronous variant: enqueues H2D, kernel and D2H on the ctx stream and returns; `leaves` is copied
+ * into pinned staging before return, `out` is valid after gai_sync(ctx).  One batch in flight per ctx. */
+int gai_loa_rollout_async(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
+                          uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id, gai_loa_result* out);
+
+/* DEVICE-resident variant (inputs already in HBM).  d_boards: n_leaves x {white,black} (16 B each,
+ * 16-byte aligned); d_stm: ceil(n/32) words, bit (i&31) of word i>>5 = side to move of leaf i;
+ * d_out: n_leaves x gai_loa_result (zeroed by the call); runs on the ctx stream, synchronises, fills stats. */
+int gai_loa_rollout_device(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves,
+                           uint32_t playouts_per_leaf, uint32_t max_plies, uint64_t philox_key,
+                           uint64_t first_playout_id, void* d_out, gai_rollout_stats* stats);
+
+/* Single playouts with full detail (tier-2 parity): per playout i (ids first_playout_id + i) from
+ * states[i]: outcome[i] in {0 white,1 black,2 draw,3 capped}, plies[i], final[i] = last position. */
+int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint32_t max_plies,
+                          uint64_t philox_key, uint64_t first_playout_id,
+                          uint8_t* outcome, uint32_t* plies, gai_loa_state* final_states);
+
+/* ---- synthetic corpus -------------------------------------------------------- */
+/* "reachable" positions: state i = the position after k_i random plies from the opening
+ * (LinesOfActionZasady.cpp:358-365), k_i = philox(key^GEN, i, 0) % max_k, moves drawn from stream
+ * (key, id = i); reaching a terminal position restarts from the opening.  Non-terminal by construction.
+ * Written to DEVICE memory in the rollout layout (d_boards, d_stm) and/or to a host state array. */
+int gai_loa_gen_reachable(gai_ctx* ctx, uint32_t n, uint64_t key, uint32_t max_k,
+                          void* d_boards, uint32_t* d_stm, gai_loa_state* host_states);
+
+/* ---- device memory helpers (so a caller without a CUDA runtime binding can stage buffers) --- */
+int gai_dev_alloc(gai_ctx* ctx, uint64_t bytes, void** d_ptr);
+int gai_dev_free(gai_ctx* ctx, void* d_ptr);
+int gai_memcpy_h2d(gai_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes);
+int gai_memcpy_d2h(gai_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes);
+/* repack reference-layout states into the device rollout layout (host side, no GPU) */
+int gai_loa_pack_states(const gai_loa_state* states, uint32_t n, void* boards16, uint32_t* stm_bits);
+
+/* ---- choice stream (host evaluation, no GPU) ------------------------------------------------ */
+/* Philox4x32-10 exactly as the kernels evaluate it (include/gameai/philox.h).  The reference draws from
+ * std::default_random_engine (MCTSPlayer.cpp:472-476, implementation-defined); the counter-based stream is
+ * what makes a playout a pure function of (key, playout id, ply). */
+void gai_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* ---- root-parallel multi-GPU (config 4) ----------------------------------------------------- */
+#define GAI_NCCL_UNIQUE_ID_BYTES 128
+/* rank 0 calls gai_comm_unique_id and ships the 128 bytes to the other ranks (any side channel). */
+int gai_comm_unique_id(uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES]);
+int gai_comm_init(gai_ctx* ctx, int rank, int world, const uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES]);
+/* Sum root-child statistics over all ranks, in place: `visits` u32[count], `values` f32[count*2]
+ * (MoveNode::numVisited / value[], MCTSPlayer.h:47-69).  One call per move decision. */
+int gai_allreduce_root(gai_ctx* ctx, uint32_t* visits, float* values, uint32_t count);
+/* Sum u64 counters over all ranks, in place (throughput bench). */
+int gai_allreduce_u64(gai_ctx* ctx, uint64_t* v, uint32_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

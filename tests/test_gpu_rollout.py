@@ -1,0 +1,117 @@
+"""GPU parity, tier 2: Philox-driven playouts bit-exact against the oracle (= reference rules driven by the
+same choice stream), through the C ABI; plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+from util import ref_corpus
+
+pytestmark = pytest.mark.gpu
+SEED = 0x10A5EED
+
+
+def test_playout_trace_vs_committed_reference(gpu):
+    G = ref_corpus()
+    o, pl, f = gpu.playout_trace(G["play_states"], 50000, int(G["seed"]), 1000)
+    assert (o == G["play_outcome"]).all() and (pl == G["play_plies"]).all() and (f == G["play_final"]).all()
+    o, pl, f = gpu.playout_trace(G["play_states"], 40, int(G["seed"]), 1000)         # ply cap
+    assert (o == G["cap_outcome"]).all() and (pl == G["cap_plies"]).all() and (f == G["cap_final"]).all()
+
+
+def test_playout_trace_vs_oracle(gpu, oracle):
+    S = np.concatenate([oracle.gen_reachable(3000, 42), oracle.gen_uniform(1000, 42)])
+    for key, first in ((1, 0), (0xDEADBEEFCAFEF00D, (1 << 40) + 5)):           # 64-bit key and ids
+        o, pl, f = gpu.playout_trace(S, 50000, key, first)
+        oo, opl, of = oracle.playout_trace_batch(S, 50000, key, first)
+        assert (o == oo).all() and (pl == opl).all() and (f == of).all()
+
+
+def test_opening_playouts(gpu, oracle):
+    S = np.tile(np.array([[0x0081818181818100, 0x7e0000000000007e, 1]], dtype=np.uint64), (2000, 1))
+    o, pl, f = gpu.playout_trace(S, 50000, SEED, 0)
+    oo, opl, of = oracle.playout_trace_batch(S, 50000, SEED, 0)
+    assert (o == oo).all() and (pl == opl).all() and (f == of).all()
+    assert 150 < pl.mean() < 280                                                # mean 213.8 plies
+
+
+@pytest.mark.parametrize("n,ppl", [(1, 1), (33, 1), (257, 7), (4096, 2), (1000, 16)])
+def test_rollout_counts_vs_oracle(gpu, oracle, n, ppl):
+    S = np.concatenate([oracle.gen_reachable(n - n // 4, 7 + n), oracle.gen_uniform(n // 4, 7 + n)]) if n > 3 else oracle.gen_reachable(n, 7)
+    counts, st = gpu.rollout(S, ppl, 50000, 0xFEED, 12345)
+    oc, oplies = oracle.rollout_states(S, ppl, 50000, 0xFEED, 12345)
+    assert (counts == oc).all()
+    assert st["playouts"] == len(S) * ppl and st["plies"] == oplies
+
+
+def test_rollout_edge_cases(gpu, oracle):
+    # empty batch
+    counts, st = gpu.rollout(np.zeros((0, 3), np.uint64), 4)
+    assert counts.shape == (0, 4) and st["playouts"] == 0
+    # terminal leaves score at 0 plies; ply cap 0 and 1
+    S = oracle.gen_uniform(512, 5)
+    t, _ = oracle.terminal_batch(S)
+    assert t.sum() > 20
+    for cap in (0, 1, 3, 17):
+        counts, st = gpu.rollout(S, 3, cap, 9, 0)
+        oc, oplies = oracle.rollout_states(S, 3, cap, 9, 0)
+        assert (counts == oc).all() and st["plies"] == oplies
+    # invalid arguments fail loudly
+    import gameai_b200 as g
+    with pytest.raises(g.GaiError):
+        gpu.rollout(S, 0)
+
+
+def test_rollout_independent_of_launch_shape(gpu, oracle):
+    """Playout identity is (leaf, playout) -> Philox counter, never the lane: any launch shape, same counts."""
+    S = oracle.gen_reachable(3000, 77)
+    ref_counts, ref_st = gpu.rollout(S, 5, 50000, 3, 0)
+    for tpb, bps in ((32, 1), (64, 3), (128, 8), (256, 2)):
+        gpu.set_launch_config(tpb, bps)
+        counts, st = gpu.rollout(S, 5, 50000, 3, 0)
+        assert (counts == ref_counts).all() and st["plies"] == ref_st["plies"]
+    gpu.set_launch_config(256, 4)
+    oc, oplies = oracle.rollout_states(S[:500], 5, 50000, 3, 0)
+    assert (ref_counts[:500] == oc).all()
+
+
+def test_device_resident_path_matches_host_path(gpu, oracle):
+    n = 5000
+    S = oracle.gen_reachable(n, 31)
+    import gameai_b200 as g
+    boards, stm = g.pack_states(S)
+    d_b = gpu.dev_alloc(boards.nbytes); d_s = gpu.dev_alloc(stm.nbytes); d_o = gpu.dev_alloc(n * 16)
+    try:
+        gpu.h2d(d_b, boards); gpu.h2d(d_s, stm)
+        st = gpu.rollout_device(d_b, d_s, n, d_o, 4, 50000, 0xAB, 10)
+        out = np.zeros((n, 4), np.uint32); gpu.d2h(out, d_o)
+        hc, hst = gpu.rollout(S, 4, 50000, 0xAB, 10)
+        assert (out == hc).all() and st["plies"] == hst["plies"]
+    finally:
+        gpu.dev_free(d_b); gpu.dev_free(d_s); gpu.dev_free(d_o)
+
+
+def test_full_size_properties_1m_leaves(gpu, oracle):
+    """Config 3 at full size (1 Mi leaves): properties that do not need the oracle at that size, plus an
+    oracle check on a strided sample of leaves (same playout ids)."""
+    n, ppl = 1 << 20, 2
+    d_b = gpu.dev_alloc(n * 16); d_s = gpu.dev_alloc(((n + 31) // 32) * 4); d_o = gpu.dev_alloc(n * 16)
+    try:
+        S = gpu.gen_reachable(n, SEED, 300, d_boards=d_b, d_stm=d_s, host=True)
+        st = gpu.rollout_device(d_b, d_s, n, d_o, ppl, 50000, SEED, 0)
+        out = np.zeros((n, 4), np.uint32); gpu.d2h(out, d_o)
+        assert (out.sum(axis=1) == ppl).all()                        # every playout accounted for exactly once
+        assert st["playouts"] == n * ppl
+        assert out[:, 3].sum() == 0                                  # nothing reaches the 50 000-ply cap
+        mean_plies = st["plies"] / st["playouts"]
+        assert 80 < mean_plies < 180
+        w, b, d = out[:, 0].sum(), out[:, 1].sum(), out[:, 2].sum()
+        assert abs(int(w) - int(b)) < 0.03 * n * ppl and d < 0.02 * n * ppl
+        # idempotence: same key/ids -> identical counts
+        st2 = gpu.rollout_device(d_b, d_s, n, d_o, ppl, 50000, SEED, 0)
+        out2 = np.zeros((n, 4), np.uint32); gpu.d2h(out2, d_o)
+        assert (out == out2).all() and st2["plies"] == st["plies"]
+        # oracle on a strided sample: leaf i's playouts have ids i*ppl + j -> reproduce with first_id = i*ppl
+        idx = np.arange(0, n, 4099)
+        for i in idx[:200]:
+            oc, _ = oracle.rollout_states(S[i:i + 1], ppl, 50000, SEED, int(i) * ppl)
+            assert (oc[0] == out[i]).all(), i
+    finally:
+        gpu.dev_free(d_b); gpu.dev_free(d_s); gpu.dev_free(d_o)
