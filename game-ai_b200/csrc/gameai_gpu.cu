@@ -42,7 +42,10 @@ struct gai_ctx {
 	cudaDeviceProp prop;
 	char err[512];
 	uint64_t launches = 0;
-	int threads = 256, blocks_per_sm = 4;
+	int threads = 256, blocks_per_sm = 4;   // baseline kernel launch shape
+	int impl = 1;                           // 0 = baseline bitboard rules (loa_rules.cuh), 1 = rotated boards + line LUT (loa_fast.cuh)
+	int fast_threads = 1024;                // one CTA per SM for the LUT kernels
+	void* d_lut = nullptr;
 	// scratch
 	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc;
 	Buf h_in, h_in2, h_out, h_out2, h_out3;
@@ -103,9 +106,14 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
 	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-	launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
-	                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
-	                   ctx->threads, rollout_grid(ctx, total), ctx->stream);
+	if (ctx->impl == 1)
+		launch_loa_rollout_fast(ctx->d_lut, d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
+		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
+		                        ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->stream);
+	else
+		launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
+		                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
+		                   ctx->threads, rollout_grid(ctx, total), ctx->stream);
 	LAUNCHED("k_rollout");
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	return GAI_OK;
@@ -157,6 +165,16 @@ int gai_create(int device, gai_ctx** out)
 		fail(nullptr, GAI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return GAI_ERR_CUDA;
 	}
 	for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+	{	// line LUT of the fast rules: built on the host from its definition, resident in HBM/L2, staged to shared memory per CTA
+		const int lb = loa_fast_lut_bytes();
+		uint16_t* h = (uint16_t*)malloc(lb);
+		loa_fast_build_lut_host(h);
+		e = cudaMalloc(&ctx->d_lut, lb);
+		if (e == cudaSuccess) e = cudaMemcpy(ctx->d_lut, h, lb, cudaMemcpyHostToDevice);
+		free(h);
+		if (e == cudaSuccess) e = loa_fast_prepare();
+		if (e != cudaSuccess) { fail(nullptr, GAI_ERR_CUDA, "line-LUT setup: %s", cudaGetErrorString(e)); gai_destroy(ctx); return GAI_ERR_CUDA; }
+	}
 	*out = ctx;
 	return GAI_OK;
 }
@@ -170,6 +188,7 @@ void gai_destroy(gai_ctx* ctx)
 	for (Buf* b : { &ctx->d_in, &ctx->d_in2, &ctx->d_out, &ctx->d_out2, &ctx->d_out3, &ctx->d_boards, &ctx->d_stm, &ctx->d_misc,
 	                &ctx->h_in, &ctx->h_in2, &ctx->h_out, &ctx->h_out2, &ctx->h_out3 }) release(*b);
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+	if (ctx->d_lut) cudaFree(ctx->d_lut);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -205,8 +224,9 @@ int gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm
 {
 	if (!ctx) return GAI_ERR_INVALID;
 	if (threads_per_block) {
-		if (threads_per_block < 32 || threads_per_block > 256 || (threads_per_block & 31)) return fail(ctx, GAI_ERR_INVALID, "threads_per_block must be a multiple of 32 in [32,256]");
-		ctx->threads = threads_per_block;
+		if (threads_per_block < 32 || threads_per_block > 1024 || (threads_per_block & 31)) return fail(ctx, GAI_ERR_INVALID, "threads_per_block must be a multiple of 32 in [32,1024]");
+		ctx->fast_threads = threads_per_block;
+		ctx->threads = threads_per_block > 256 ? 256 : threads_per_block;
 	}
 	if (blocks_per_sm) {
 		if (blocks_per_sm < 1 || blocks_per_sm > 32) return fail(ctx, GAI_ERR_INVALID, "blocks_per_sm must be in [1,32]");
@@ -216,6 +236,14 @@ int gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm
 }
 
 uint64_t gai_launch_count(const gai_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gai_set_rules_impl(gai_ctx* ctx, int impl)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (impl != 0 && impl != 1) return fail(ctx, GAI_ERR_INVALID, "rules impl must be 0 (bitboard baseline) or 1 (rotated boards + line LUT)");
+	ctx->impl = impl;
+	return GAI_OK;
+}
 
 // ---- rules sweep ---------------------------------------------------------------------------------
 int gai_loa_movegen(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8_t* counts, gai_loa_move* moves)
@@ -228,7 +256,8 @@ int gai_loa_movegen(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, mb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemsetAsync(ctx->d_out2.p, 0, mb, ctx->stream));
-	launch_loa_movegen(ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->stream);
+	if (ctx->impl == 1) launch_loa_movegen_fast(ctx->d_lut, ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->prop.multiProcessorCount, ctx->stream);
+	else launch_loa_movegen(ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->stream);
 	LAUNCHED("k_movegen");
 	CU(cudaMemcpyAsync(counts, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(moves, ctx->d_out2.p, mb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -279,10 +308,17 @@ int gai_loa_successor_hash(gai_ctx* ctx, const gai_loa_state* states, uint32_t n
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, (size_t)n * 8, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
-	launch_loa_successor_hash(ctx->d_in.p, n, (uint64_t*)ctx->d_out.p, ctx->stream);
+	uint32_t bad = 0;
+	if (ctx->impl == 1) {
+		EN(ctx->d_misc, 64, false);
+		CU(cudaMemsetAsync((char*)ctx->d_misc.p + 32, 0, 4, ctx->stream));
+		launch_loa_successor_hash_fast(ctx->d_lut, ctx->d_in.p, n, (uint64_t*)ctx->d_out.p, (uint32_t*)((char*)ctx->d_misc.p + 32), ctx->prop.multiProcessorCount, ctx->stream);
+	} else launch_loa_successor_hash(ctx->d_in.p, n, (uint64_t*)ctx->d_out.p, ctx->stream);
 	LAUNCHED("k_successor_hash");
 	CU(cudaMemcpyAsync(hash, ctx->d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->impl == 1) CU(cudaMemcpyAsync(&bad, (char*)ctx->d_misc.p + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	if (bad) return fail(ctx, GAI_ERR_CUDA, "rotated boards diverged from the plain bitboard after apply (internal consistency check)");
 	return GAI_OK;
 }
 
@@ -362,10 +398,12 @@ int gai_loa_rollout_device(gai_ctx* ctx, const void* d_boards, const uint32_t* d
 	if (!d_boards || !d_stm || !d_out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_device: NULL buffer");
 	if (playouts_per_leaf == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_device: playouts_per_leaf must be >= 1");
 	CU(cudaSetDevice(ctx->device));
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 	int r = enqueue_rollout(ctx, d_boards, d_stm, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id, d_out);
 	if (r) return r;
+	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	return fill_stats(ctx, stats, false);
+	return fill_stats(ctx, stats, true);
 }
 
 int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint32_t max_plies,
@@ -379,8 +417,12 @@ int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n,
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 4, false); EN(ctx->d_out3, sb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
-	launch_loa_playout_trace(ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
-	                         (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->stream);
+	if (ctx->impl == 1)
+		launch_loa_playout_trace_fast(ctx->d_lut, ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
+		                              (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->prop.multiProcessorCount, ctx->stream);
+	else
+		launch_loa_playout_trace(ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
+		                         (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->stream);
 	LAUNCHED("k_playout_trace");
 	CU(cudaMemcpyAsync(outcome, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(plies, ctx->d_out2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

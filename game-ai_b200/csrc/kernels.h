@@ -17,3 +17,15 @@ void launch_loa_playout_trace(const void* d_states, uint32_t n, uint32_t max_pli
 void launch_loa_gen_reachable(uint32_t n, uint64_t key, uint32_t max_k, void* d_boards, void* d_states24, uint8_t* d_side, cudaStream_t st);
 void launch_loa_pack_stm(const uint8_t* d_side, uint32_t n, uint32_t* d_stm, cudaStream_t st);
 void launch_loa_split_states(const void* d_states24, uint32_t n, void* d_boards, uint32_t* d_stm, cudaStream_t st);
+
+// "rotated boards + line LUT" formulation (loa_fast.cuh): one CTA per SM, LUT in shared memory
+int  loa_fast_lut_bytes();
+void loa_fast_build_lut_host(uint16_t* lut);
+cudaError_t loa_fast_prepare();
+void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+                             uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
+                             int threads, int sms, cudaStream_t st);
+void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st);
+void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uint32_t n, uint64_t* d_hash, uint32_t* d_bad, int sms, cudaStream_t st);
+void launch_loa_playout_trace_fast(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
+                                   uint8_t* d_outcome, uint32_t* d_plies, void* d_final, int sms, cudaStream_t st);

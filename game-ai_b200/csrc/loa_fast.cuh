@@ -1,0 +1,153 @@
+// game-ai_b200/csrc/loa_fast.cuh -- LOA rules, "rotated boards + line LUT" formulation (device).
+//
+// Same observable behaviour as loa_rules.cuh / LinesOfActionZasady.cpp:136-232 (move ORDER included), but
+// organised for the B200 SM: the path is ALU-pipe bound (LOP3/SHF/IADD issue at half rate), so per piece the
+// work is four shared-memory lookups instead of ~150 bit operations:
+//
+//  * each colour is held in four 64-bit "rotated" boards in registers, so that every line through a square is
+//    ONE BYTE of one register pair:
+//        R  : byte = row r          cell = column c           (the plain bitboard, LinesOfActionZasady.cpp:43)
+//        C  : byte = column c       cell = 7 - r              (transposed, rows reversed)
+//        D1 : byte = (r - c) & 7    cell = column c           ("left" diagonal A1->H8, :93-113)
+//        D2 : byte = (r + c) & 7    cell = row r              ("right" diagonal H1->A8, :114-135)
+//    The cell orientation is chosen so that in all four the reference's FIRST direction of the line
+//    (W, N, SW, SE -- :194-223) is "towards lower cells" and the second (E, S, NE, NW) "towards higher cells".
+//    A D1/D2 byte holds two complementary diagonals (lengths k and 8-k); the cells of the other diagonal are
+//    presented to the LUT as "phantom" cells.
+//  * one table LUT[(o8, e8)] (own / enemy occupancy of the 8 cells) -> 16 bits, 2 per cell:
+//    bit 2p = own piece on cell p may move towards lower cells, bit 2p+1 = towards higher cells, by the
+//    number of pieces on the line (:191-192), not landing on an own piece (:142), not jumping an enemy
+//    (:146-148).  A cell with BOTH o and e set is a phantom: not counted, not a mover, cannot be landed on.
+//    Index = o8 + 258*e8 (the odd stride spreads (o,e) pairs over the 32 shared-memory banks).
+#pragma once
+#include "loa_rules.cuh"
+
+namespace loa {
+
+constexpr int LUT_STRIDE = 258;
+constexpr int LUT_ENTRIES = LUT_STRIDE * 255 + 256;          // 66046
+constexpr int LUT_BYTES = ((LUT_ENTRIES * 2 + 15) / 16) * 16; // 132096
+
+// One LUT entry, by definition (host + device; the table is built once per context on the host).
+__host__ __device__ inline uint16_t lut_entry(u32 o, u32 e)
+{
+	const u32 own = o & ~e, enemy = e & ~o;
+	int n = 0;
+	for (int i = 0; i < 8; ++i) n += ((own | enemy) >> i) & 1u;
+	u32 res = 0;
+	for (int p = 0; p < 8; ++p) {
+		if (!((own >> p) & 1u)) continue;
+		const int tu = p + n, td = p - n;
+		if (tu < 8 && !((o >> tu) & 1u)) {                 // on the line, not own, not phantom
+			bool blocked = false;
+			for (int q = p + 1; q < tu; ++q) blocked |= (enemy >> q) & 1u;
+			if (!blocked) res |= 2u << (2 * p);
+		}
+		if (td >= 0 && !((o >> td) & 1u)) {
+			bool blocked = false;
+			for (int q = td + 1; q < p; ++q) blocked |= (enemy >> q) & 1u;
+			if (!blocked) res |= 1u << (2 * p);
+		}
+	}
+	return (uint16_t)res;
+}
+
+// rotated-board bit positions of square s = 8r + c
+__host__ __device__ constexpr int pos_c(int s)  { return 8 * (s & 7) + (7 - (s >> 3)); }
+__host__ __device__ constexpr int pos_d1(int s) { return 8 * (((s >> 3) - (s & 7)) & 7) + (s & 7); }
+__host__ __device__ constexpr int pos_d2(int s) { return 8 * (((s >> 3) + (s & 7)) & 7) + (s >> 3); }
+// phantom cells of the D1 / D2 byte seen from square s (cells that belong to the complementary diagonal)
+__host__ __device__ constexpr u32 phantom_d1(int s)
+{
+	const int r = s >> 3, c = s & 7, k = (r - c) & 7;
+	return (r >= c) ? ((0xffu << (8 - k)) & 0xffu) : ((1u << (8 - k)) - 1u);
+}
+__host__ __device__ constexpr u32 phantom_d2(int s)
+{
+	const int r = s >> 3, c = s & 7, k = (r + c) & 7;
+	return (r + c <= 7) ? ((0xffu << (k + 1)) & 0xffu) : ((1u << (k + 1)) - 1u);
+}
+
+// per-square constants, one 64-bit word:  lo = phD1 | phD2<<8 | byteD1<<16 | byteD2<<24 ; hi = posC | posD1<<8 | posD2<<16
+struct SquareTable { u64 w[64]; };
+__host__ __device__ constexpr SquareTable make_square_table()
+{
+	SquareTable t{};
+	for (int s = 0; s < 64; ++s) {
+		const u64 lo = (u64)phantom_d1(s) | ((u64)phantom_d2(s) << 8) | ((u64)(pos_d1(s) >> 3) << 16) | ((u64)(pos_d2(s) >> 3) << 24);
+		const u64 hi = (u64)pos_c(s) | ((u64)pos_d1(s) << 8) | ((u64)pos_d2(s) << 16);
+		t.w[s] = lo | (hi << 32);
+	}
+	return t;
+}
+
+struct Side { u64 R, C, D1, D2; };      // one colour, four rotations
+
+__device__ __forceinline__ u64 bit64(int p) { return 1ull << p; }
+
+// build the rotations of one colour from its plain bitboard (once per playout)
+__device__ __forceinline__ Side make_side(u64 b, const u64* __restrict__ sqt)
+{
+	Side s; s.R = b; s.C = 0; s.D1 = 0; s.D2 = 0;
+	for (u64 rest = b; rest; rest &= rest - 1) {
+		const int q = __ffsll((long long)rest) - 1;
+		const u32 hi = (u32)(sqt[q] >> 32);
+		s.C |= bit64(hi & 63u); s.D1 |= bit64((hi >> 8) & 63u); s.D2 |= bit64((hi >> 16) & 63u);
+	}
+	return s;
+}
+
+__device__ __forceinline__ u32 byte_of(u64 x, u32 i) { return __byte_perm((u32)x, (u32)(x >> 32), i); }   // byte i in bits 0..7, junk above
+
+// LUT address (in bytes) of the line with own/enemy occupancy bytes po/pe (junk above bit 7) and phantom cells ph
+__device__ __forceinline__ u32 lut_lookup(const uint16_t* __restrict__ lut, u32 po, u32 pe, u32 ph)
+{
+	const u32 o = (po & 0xffu) | ph, e = (pe & 0xffu) | ph;
+	return lut[o + e * (u32)LUT_STRIDE];
+}
+
+// 8-bit move mask (bit d = reference direction d legal) of the own piece on square s
+__device__ __forceinline__ u32 piece_moves_fast(const Side& my, const Side& en, int s, const uint16_t* __restrict__ lut,
+                                                const u64* __restrict__ sqt)
+{
+	const u32 r = (u32)s >> 3, c = (u32)s & 7u;
+	const u32 t = (u32)sqt[s];
+	const u32 ph1 = __byte_perm(t, 0, 0x4440), ph2 = __byte_perm(t, 0, 0x4441);
+	const u32 k1 = __byte_perm(t, 0, 0x4442), k2 = __byte_perm(t, 0, 0x4443);
+	const u32 vR = lut_lookup(lut, byte_of(my.R, r), byte_of(en.R, r), 0u);
+	const u32 vC = lut_lookup(lut, byte_of(my.C, c), byte_of(en.C, c), 0u);
+	const u32 v1 = lut_lookup(lut, byte_of(my.D1, k1), byte_of(en.D1, k1), ph1);
+	const u32 v2 = lut_lookup(lut, byte_of(my.D2, k2), byte_of(en.D2, k2), ph2);
+	const u32 xR = (vR >> (2u * c)) & 3u;            // W, E
+	const u32 xC = (vC >> (14u - 2u * r)) & 3u;      // N, S
+	const u32 x1 = (v1 >> (2u * c)) & 3u;            // SW, NE
+	const u32 x2 = (v2 >> (2u * r)) & 3u;            // SE, NW
+	return xR + xC * 4u + x1 * 16u + x2 * 64u;
+}
+
+__device__ __forceinline__ MoveMasks all_piece_moves_fast(const Side& my, const Side& en, const uint16_t* __restrict__ lut,
+                                                          const u64* __restrict__ sqt)
+{
+	MoveMasks m; m.lo = 0; m.hi = 0;
+	int j = 0;
+	for (u64 rest = my.R; rest; rest &= rest - 1, ++j) {
+		const int s = __ffsll((long long)rest) - 1;
+		const u64 v = piece_moves_fast(my, en, s, lut, sqt);
+		if (j < 8) m.lo |= v << (8 * j); else m.hi |= v << (8 * (j - 8));
+	}
+	return m;
+}
+
+// move the own piece from -> to in all four rotations; captures the enemy piece on `to` if any
+__device__ __forceinline__ void apply_move_fast(Side& my, Side& en, int from, int to, const u64* __restrict__ sqt)
+{
+	const u32 hf = (u32)(sqt[from] >> 32), ht = (u32)(sqt[to] >> 32);
+	const u64 tR = bit64(to), tC = bit64(ht & 63u), t1 = bit64((ht >> 8) & 63u), t2 = bit64((ht >> 16) & 63u);
+	my.R = (my.R ^ bit64(from)) | tR;
+	my.C = (my.C ^ bit64(hf & 63u)) | tC;
+	my.D1 = (my.D1 ^ bit64((hf >> 8) & 63u)) | t1;
+	my.D2 = (my.D2 ^ bit64((hf >> 16) & 63u)) | t2;
+	en.R &= ~tR; en.C &= ~tC; en.D1 &= ~t1; en.D2 &= ~t2;
+}
+
+} // namespace loa

@@ -1,0 +1,232 @@
+// game-ai_b200/csrc/loa_fast_kernels.cu -- rollout / sweep kernels on the "rotated boards + line LUT" rules.
+// One CTA per SM (the 129 KB line LUT lives in shared memory), persistent, one playout per thread.
+#include "loa_fast.cuh"
+#include "loa_sim.cuh"
+#include "kernels.h"
+
+namespace loa {
+
+__constant__ DiagTables c_diag2 = make_diag_tables();
+__constant__ SquareTable c_sqt = make_square_table();
+
+struct FastSmem {
+	const uint16_t* lut; const u64* sqt; const u64* ld; const u64* rd;
+};
+
+// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][64 x u64 ld][64 x u64 rd]
+constexpr int FAST_SMEM_BYTES = LUT_BYTES + 3 * 64 * 8;
+
+__device__ __forceinline__ FastSmem load_fast_smem(unsigned char* smem, const uint4* __restrict__ g_lut)
+{
+	uint4* d = reinterpret_cast<uint4*>(smem);
+	for (int i = threadIdx.x; i < LUT_BYTES / 16; i += blockDim.x) d[i] = __ldg(g_lut + i);
+	u64* sq = reinterpret_cast<u64*>(smem + LUT_BYTES);
+	for (int i = threadIdx.x; i < 64; i += blockDim.x) { sq[i] = c_sqt.w[i]; sq[64 + i] = c_diag2.ld[i]; sq[128 + i] = c_diag2.rd[i]; }
+	__syncthreads();
+	FastSmem f; f.lut = reinterpret_cast<const uint16_t*>(smem); f.sqt = sq; f.ld = sq + 64; f.rd = sq + 128;
+	return f;
+}
+
+struct FastSim {
+	Side my, en;       // side to move / side that just moved
+	u32 side, ply, rq;
+	bool chk_en, chk_my;
+};
+
+__device__ __forceinline__ void fsim_init(FastSim& s, u64 white, u64 black, u32 side, const FastSmem& f)
+{
+	s.side = side & 1u;
+	s.my = make_side(s.side ? black : white, f.sqt);
+	s.en = make_side(s.side ? white : black, f.sqt);
+	s.ply = 0; s.rq = 0xffffffffu;
+	s.chk_en = true; s.chk_my = true;
+}
+
+// one ply; -1 while the playout continues, else the outcome code (same semantics as loa_sim.cuh sim_step)
+__device__ __forceinline__ int fsim_step(FastSim& s, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies, const FastSmem& f)
+{
+	const bool c_en = s.chk_en && connected_fast(s.en.R);
+	const bool c_my = s.chk_my && connected_fast(s.my.R);
+	if (c_en | c_my) {
+		const bool wc = s.side ? c_en : c_my, bc = s.side ? c_my : c_en;
+		return outcome_of(wc, bc);
+	}
+	if (s.ply >= max_plies) return OUT_CAPPED;
+
+	const MoveMasks m = all_piece_moves_fast(s.my, s.en, f.lut, f.sqt);
+	const u32 n = (u32)count_moves(m);
+	bool cap = false, moved = false;
+	if (n != 0) {
+		if ((s.ply >> 2) != s.rq) { s.rq = s.ply >> 2; rnd = gai::choice_block(key, id, s.rq); }
+		const u32 idx = gai::choice_index(pick_word(rnd, s.ply), n);
+		int from, to;
+		nth_move(m, s.my.R, s.en.R, idx, f.ld, f.rd, &from, &to);
+		cap = (s.en.R >> to) & 1ull;
+		apply_move_fast(s.my, s.en, from, to, f.sqt);
+		moved = true;
+	}
+	const Side t = s.my; s.my = s.en; s.en = t;
+	s.side ^= 1u;
+	s.ply += 1;
+	s.chk_en = moved; s.chk_my = cap;
+	return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ boards, const u32* __restrict__ stm,
+               u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
+               u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem(smem, g_lut);
+
+	const u64 total = (u64)n_leaves * ppl;
+	const u32 lane = threadIdx.x & 31u;
+	FastSim s; gai::Philox4 rnd;
+	u64 item = 0; u32 leaf = 0;
+	bool need = true;
+	u64 my_plies = 0, my_playouts = 0;
+	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
+
+	for (;;) {
+		if (need) {
+			const unsigned grp = __activemask();
+			const int leader = __ffs(grp) - 1;
+			unsigned long long base = 0;
+			if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(grp));
+			base = __shfl_sync(grp, base, leader);
+			item = base + __popc(grp & ((1u << lane) - 1u));
+			if (item >= total) break;
+			leaf = (u32)(item / ppl);
+			const ulonglong2 bd = __ldg(boards + leaf);
+			const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
+			fsim_init(s, bd.x, bd.y, side, f);
+			need = false;
+		}
+		const int o = fsim_step(s, rnd, key, first_id + item, max_plies, f);
+		if (o >= 0) {
+			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
+			my_plies += s.ply; my_playouts += 1;
+			need = true;
+		}
+	}
+	__syncwarp();
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		my_plies += __shfl_xor_sync(0xffffffffu, my_plies, d);
+		my_playouts += __shfl_xor_sync(0xffffffffu, my_playouts, d);
+	}
+	if (lane == 0) { atomicAdd((unsigned long long*)stats, my_playouts); atomicAdd((unsigned long long*)stats + 1, my_plies); }
+}
+
+// tier-1 sweep through the SAME movegen the rollout kernel uses (persistent grid-stride, one CTA per SM)
+__global__ void __launch_bounds__(1024, 1)
+k_movegen_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, uint8_t* __restrict__ counts, uint8_t* __restrict__ moves)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem(smem, g_lut);
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const u64 w = states[3 * (size_t)i], b = states[3 * (size_t)i + 1];
+		const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
+		const Side my = make_side(side ? b : w, f.sqt), en = make_side(side ? w : b, f.sqt);
+		const MoveMasks m = all_piece_moves_fast(my, en, f.lut, f.sqt);
+		const u32 cnt = (u32)count_moves(m);
+		counts[i] = (uint8_t)cnt;
+		uint8_t* outp = moves + (size_t)i * 2 * GAI_LOA_MAX_MOVES_K;
+		for (u32 k = 0; k < cnt && k < GAI_LOA_MAX_MOVES_K; ++k) {
+			int from, to;
+			nth_move(m, my.R, en.R, k, f.ld, f.rd, &from, &to);
+			outp[2 * k] = (uint8_t)from; outp[2 * k + 1] = (uint8_t)to;
+		}
+	}
+}
+
+// successor hash through apply_move_fast: checks all four rotations stay consistent with the plain board
+__global__ void __launch_bounds__(1024, 1)
+k_successor_hash_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, u64* __restrict__ hash, u32* __restrict__ bad)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem(smem, g_lut);
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const u64 w = states[3 * (size_t)i], b = states[3 * (size_t)i + 1];
+		const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
+		const Side my = make_side(side ? b : w, f.sqt), en = make_side(side ? w : b, f.sqt);
+		const MoveMasks m = all_piece_moves_fast(my, en, f.lut, f.sqt);
+		const u32 cnt = (u32)count_moves(m);
+		u64 h = 0;
+		for (u32 k = 0; k < cnt; ++k) {
+			int from, to;
+			nth_move(m, my.R, en.R, k, f.ld, f.rd, &from, &to);
+			Side nmy = my, nen = en;
+			apply_move_fast(nmy, nen, from, to, f.sqt);
+			// rotations must equal a fresh rebuild from the plain board
+			const Side cm = make_side(nmy.R, f.sqt), ce = make_side(nen.R, f.sqt);
+			if (cm.C != nmy.C || cm.D1 != nmy.D1 || cm.D2 != nmy.D2 || ce.C != nen.C || ce.D1 != nen.D1 || ce.D2 != nen.D2) atomicAdd(bad, 1u);
+			const u64 nw = side ? nen.R : nmy.R, nb = side ? nmy.R : nen.R;
+			const bool wc = connected_fast(nw), bc = connected_fast(nb);
+			h = (h ^ nw); h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31;
+			h = (h ^ nb); h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31;
+			h = h ^ ((u64)(side ^ 1u) | ((u64)k << 8) | ((u64)(wc ? 1 : 0) << 16) | ((u64)(bc ? 1 : 0) << 17));
+			h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31;
+		}
+		hash[i] = h;
+	}
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_playout_trace_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, u32 max_plies, u64 key, u64 first_id,
+                     uint8_t* __restrict__ outcome, u32* __restrict__ plies, u64* __restrict__ final_states)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem(smem, g_lut);
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		FastSim s; gai::Philox4 rnd;
+		fsim_init(s, states[3 * (size_t)i], states[3 * (size_t)i + 1], (u32)states[3 * (size_t)i + 2] & 1u, f);
+		int o;
+		do { o = fsim_step(s, rnd, key, first_id + i, max_plies, f); } while (o < 0);
+		outcome[i] = (uint8_t)o;
+		plies[i] = s.ply;
+		final_states[3 * (size_t)i] = s.side ? s.en.R : s.my.R;
+		final_states[3 * (size_t)i + 1] = s.side ? s.my.R : s.en.R;
+		final_states[3 * (size_t)i + 2] = s.side;
+	}
+}
+
+} // namespace loa
+
+using namespace loa;
+
+int loa_fast_lut_bytes() { return LUT_BYTES; }
+void loa_fast_build_lut_host(uint16_t* lut)
+{
+	for (int i = 0; i < LUT_BYTES / 2; ++i) lut[i] = 0;
+	for (u32 e = 0; e < 256; ++e)
+		for (u32 o = 0; o < 256; ++o) lut[o + e * LUT_STRIDE] = lut_entry(o, e);
+}
+cudaError_t loa_fast_prepare()
+{
+	cudaError_t e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_movegen_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_successor_hash_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	return cudaFuncSetAttribute(k_playout_trace_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+}
+static int fast_grid(uint32_t n, int threads, int sms) { const int need = (int)((n + threads - 1) / threads); return need < sms ? (need ? need : 1) : sms; }
+
+void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+                             uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
+                             int threads, int sms, cudaStream_t st)
+{
+	const uint64_t total = (uint64_t)n_leaves * ppl;
+	const int blocks = fast_grid(total > 0xffffffffull ? 0xffffffffu : (uint32_t)total, threads, sms);
+	k_rollout_fast<<<blocks, threads, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, n_leaves, ppl, max_plies,
+	                                                          key, first_id, d_out, (u64*)d_stats, d_counter);
+}
+void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
+{ if (n) k_movegen_fast<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
+void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uint32_t n, uint64_t* d_hash, uint32_t* d_bad, int sms, cudaStream_t st)
+{ if (n) k_successor_hash_fast<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, (u64*)d_hash, d_bad); }
+void launch_loa_playout_trace_fast(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
+                                   uint8_t* d_outcome, uint32_t* d_plies, void* d_final, int sms, cudaStream_t st)
+{ if (n) k_playout_trace_fast<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, max_plies, key, first_id, d_outcome, d_plies, (u64*)d_final); }

@@ -29,9 +29,12 @@ def ref_oracle():
     return r
 
 
-@pytest.fixture(scope="session")
-def gpu():
+@pytest.fixture(scope="session", params=[1, 0], ids=["lut", "bitboard"])
+def gpu(request):
+    """The engine, once per device formulation of the rules (both must be bit-exact against the oracle)."""
     import gameai_b200 as g
     eng = g.GpuRollout(0)      # raises loudly without a device / library: no fallback
+    eng.set_rules_impl(request.param)
+    eng.impl = request.param
     yield eng
     eng.close()

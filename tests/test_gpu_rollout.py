@@ -63,11 +63,11 @@ def test_rollout_independent_of_launch_shape(gpu, oracle):
     """Playout identity is (leaf, playout) -> Philox counter, never the lane: any launch shape, same counts."""
     S = oracle.gen_reachable(3000, 77)
     ref_counts, ref_st = gpu.rollout(S, 5, 50000, 3, 0)
-    for tpb, bps in ((32, 1), (64, 3), (128, 8), (256, 2)):
+    for tpb, bps in ((32, 1), (64, 3), (128, 8), (256, 2), (512, 1), (1024, 1)):
         gpu.set_launch_config(tpb, bps)
         counts, st = gpu.rollout(S, 5, 50000, 3, 0)
         assert (counts == ref_counts).all() and st["plies"] == ref_st["plies"]
-    gpu.set_launch_config(256, 4)
+    gpu.set_launch_config(1024, 4)
     oc, oplies = oracle.rollout_states(S[:500], 5, 50000, 3, 0)
     assert (ref_counts[:500] == oc).all()
 
