@@ -47,7 +47,7 @@ struct gai_ctx {
 	int fast_threads = 1024;                // one CTA per SM for the LUT kernels
 	void* d_lut = nullptr;
 	// scratch
-	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc;
+	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc, d_prep;
 	Buf h_in, h_in2, h_out, h_out2, h_out3;
 	// async rollout bookkeeping
 	gai_loa_result* pending_out = nullptr; uint32_t pending_n = 0;
@@ -102,15 +102,19 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
                     uint32_t max_plies, uint64_t key, uint64_t first_id, void* d_out)
 {
 	EN(ctx->d_misc, 64, false);
+	if (ctx->impl == 1) EN(ctx->d_prep, (size_t)n_leaves * 64, false);
 	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
 	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-	if (ctx->impl == 1)
-		launch_loa_rollout_fast(ctx->d_lut, d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
+	if (ctx->impl == 1) {
+		// rotations of every leaf, once per batch (inside the timed region: it is part of the step)
+		launch_loa_prepare_leaves(d_boards, n_leaves, ctx->d_prep.p, ctx->stream);
+		LAUNCHED("k_prepare_leaves");
+		launch_loa_rollout_fast(ctx->d_lut, ctx->d_prep.p, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
 		                        ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->stream);
-	else
+	} else
 		launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
 		                   ctx->threads, rollout_grid(ctx, total), ctx->stream);
@@ -185,7 +189,7 @@ void gai_destroy(gai_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
-	for (Buf* b : { &ctx->d_in, &ctx->d_in2, &ctx->d_out, &ctx->d_out2, &ctx->d_out3, &ctx->d_boards, &ctx->d_stm, &ctx->d_misc,
+	for (Buf* b : { &ctx->d_in, &ctx->d_in2, &ctx->d_out, &ctx->d_out2, &ctx->d_out3, &ctx->d_boards, &ctx->d_stm, &ctx->d_misc, &ctx->d_prep,
 	                &ctx->h_in, &ctx->h_in2, &ctx->h_out, &ctx->h_out2, &ctx->h_out3 }) release(*b);
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->d_lut) cudaFree(ctx->d_lut);

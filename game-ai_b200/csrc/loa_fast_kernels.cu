@@ -13,8 +13,9 @@ struct FastSmem {
 	const uint16_t* lut; const u64* sqt; const u64* ld; const u64* rd;
 };
 
-// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][64 x u64 ld][64 x u64 rd]
-constexpr int FAST_SMEM_BYTES = LUT_BYTES + 3 * 64 * 8;
+// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][64 x u64 ld][64 x u64 rd][16 x 1024 bytes piece squares]
+constexpr int FAST_SQ_OFF = LUT_BYTES + 3 * 64 * 8;
+constexpr int FAST_SMEM_BYTES = FAST_SQ_OFF + 16 * 1024;
 
 __device__ __forceinline__ FastSmem load_fast_smem(unsigned char* smem, const uint4* __restrict__ g_lut)
 {
@@ -73,8 +74,112 @@ __device__ __forceinline__ int fsim_step(FastSim& s, gai::Philox4& rnd, u64 key,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-synchronous playout step.  All 32 lanes of a warp execute every phase together; a lane without work in a
+// phase is predicated off.  Data-dependent loops (pieces of the side to move, flood-fill iterations) run for the
+// warp-wide maximum trip count under a __any_sync condition, so the warp reconverges every iteration instead of
+// splitting into independently scheduled fragments (ncu on the lane-independent version: 9.8 of 32 lanes active,
+// the piece loop body issued 17.8x per warp-ply for at most 12 pieces).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+// calcIfTerminal (LinesOfActionZasady.cpp:52-58) for the lanes with want == true
+__device__ __forceinline__ bool wconnected(u64 b, bool want)
+{
+	bool res = false;
+	bool pend = want && b != 0;
+	if (pend && (b & (b - 1)) == 0) { res = true; pend = false; }       // exactly one piece
+	if (pend && has_isolated_piece(b)) pend = false;                    // >= 2 pieces, one with no neighbour
+	u64 g = b & (0 - b);
+	while (__any_sync(FULL, pend)) {
+		if (pend) {
+			const u64 n = dilate8(g) & b;
+			if (n == g) { pend = false; res = (g == b); }
+			g = n;
+		}
+	}
+	return res;
+}
+
+// One ply for every lane with alive == true.  Returns the outcome code for lanes whose playout ended in this
+// step, -1 otherwise (also for lanes that were not alive).
+__device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies, const FastSmem& f,
+                                     unsigned char* __restrict__ sq_scratch)
+{
+	const bool c_en = wconnected(s.en.R, alive && s.chk_en);
+	bool c_my = false;
+	if (__any_sync(FULL, alive && s.chk_my)) c_my = wconnected(s.my.R, alive && s.chk_my);
+	const bool term = c_en | c_my;
+	const bool capped = alive && !term && s.ply >= max_plies;
+	const bool play = alive && !term && !capped;
+	int result = -1;
+	if (term) { const bool wc = s.side ? c_en : c_my, bc = s.side ? c_my : c_en; result = outcome_of(wc, bc); }
+	if (capped) result = OUT_CAPPED;
+
+	// move generation: per own piece four LUT lookups; all lanes iterate for the warp-wide maximum piece count
+	// (one REDUX), the piece's square is parked in shared memory ([piece][thread] bytes, conflict-free)
+	u64 rest = play ? s.my.R : 0ull;
+	const int maxp = __reduce_max_sync(FULL, __popcll(rest));
+	u32 m0 = 0, m1 = 0, m2 = 0, m3 = 0;          // move masks, pieces 0-3 / 4-7 / 8-11 / 12-15, one byte per piece
+	unsigned char* sqp = sq_scratch + threadIdx.x;
+	for (int j = 0; j < maxp; ++j) {
+		if (rest != 0) {
+			const int sq = __ffsll((long long)rest) - 1;
+			rest &= rest - 1;
+			const u32 v = piece_moves_fast(s.my, s.en, sq, f.lut, f.sqt) << (8 * (j & 3));
+			sqp[j * 1024] = (unsigned char)sq;
+			if (j < 4) m0 |= v; else if (j < 8) m1 |= v; else if (j < 12) m2 |= v; else m3 |= v;
+		}
+	}
+	if (play) {
+		const u32 c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+		const u32 n = c0 + c1 + c2 + c3;
+		bool cap = false, moved = false;
+		if (n != 0) {
+			if ((s.ply >> 2) != s.rq) { s.rq = s.ply >> 2; rnd = gai::choice_block(key, id, s.rq); }
+			u32 k = gai::choice_index(pick_word(rnd, s.ply), n);
+			// rank-select, branch free: which word, then 5 halving steps inside the word
+			u32 x = m0; int base = 0;
+			{ const bool g = k >= c0; k -= g ? c0 : 0u; x = g ? m1 : x; base = g ? 32 : base;
+			  const bool g1 = g && k >= c1; k -= g1 ? c1 : 0u; x = g1 ? m2 : x; base = g1 ? 64 : base;
+			  const bool g2 = g1 && k >= c2; k -= g2 ? c2 : 0u; x = g2 ? m3 : x; base = g2 ? 96 : base; }
+			int pos = 0;
+			{ u32 c = __popc(x & 0xffffu); bool g = k >= c; k -= g ? c : 0u; pos += g ? 16 : 0; x = g ? x >> 16 : x;
+			  c = __popc(x & 0xffu); g = k >= c; k -= g ? c : 0u; pos += g ? 8 : 0; x = g ? x >> 8 : x;
+			  c = __popc(x & 0xfu); g = k >= c; k -= g ? c : 0u; pos += g ? 4 : 0; x = g ? x >> 4 : x;
+			  c = __popc(x & 0x3u); g = k >= c; k -= g ? c : 0u; pos += g ? 2 : 0; x = g ? x >> 2 : x;
+			  pos += (k >= (x & 1u)) ? 1 : 0; }
+			const int bit = base + pos;
+			const int from = sqp[(bit >> 3) * 1024];
+			const int to = move_target(s.my.R | s.en.R, from, bit & 7, f.ld, f.rd);
+			cap = (s.en.R >> to) & 1ull;
+			apply_move_fast(s.my, s.en, from, to, f.sqt);
+			moved = true;
+		}
+		const Side t = s.my; s.my = s.en; s.en = t;
+		s.side ^= 1u;
+		s.ply += 1;
+		s.chk_en = moved; s.chk_my = cap;
+	}
+	return result;
+}
+
+// Leaf preparation: the four rotations of both colours, once per leaf (64 B = 4 x 16-byte vectors), so that a
+// lane that pulls a new playout issues four LDG.128 instead of rebuilding the rotations piece by piece while the
+// other 31 lanes of its warp wait (ncu: 6 % of all issued instructions at 1 active lane before this kernel existed).
+__global__ void k_prepare_leaves(const ulonglong2* __restrict__ boards, u32 n, ulonglong2* __restrict__ prep)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const ulonglong2 bd = boards[i];
+	const Side w = make_side(bd.x, c_sqt.w), b = make_side(bd.y, c_sqt.w);
+	prep[4 * (size_t)i + 0] = make_ulonglong2(w.R, w.C);
+	prep[4 * (size_t)i + 1] = make_ulonglong2(w.D1, w.D2);
+	prep[4 * (size_t)i + 2] = make_ulonglong2(b.R, b.C);
+	prep[4 * (size_t)i + 3] = make_ulonglong2(b.D1, b.D2);
+}
+
 __global__ void __launch_bounds__(1024, 1)
-k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ boards, const u32* __restrict__ stm,
+k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm,
                u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
                u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
 {
@@ -85,37 +190,46 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ b
 	const u32 lane = threadIdx.x & 31u;
 	FastSim s; gai::Philox4 rnd;
 	u64 item = 0; u32 leaf = 0;
-	bool need = true;
+	bool need = true, exhausted = false;
 	u64 my_plies = 0, my_playouts = 0;
 	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
+	rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
 
 	for (;;) {
-		if (need) {
-			const unsigned grp = __activemask();
-			const int leader = __ffs(grp) - 1;
+		// refill: lanes whose playout ended pull the next (leaf, playout) item; one atomic per warp per refill round
+		const unsigned needmask = __ballot_sync(FULL, need && !exhausted);
+		if (needmask) {
+			const int leader = __ffs(needmask) - 1;
 			unsigned long long base = 0;
-			if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(grp));
-			base = __shfl_sync(grp, base, leader);
-			item = base + __popc(grp & ((1u << lane) - 1u));
-			if (item >= total) break;
-			leaf = (u32)(item / ppl);
-			const ulonglong2 bd = __ldg(boards + leaf);
-			const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
-			fsim_init(s, bd.x, bd.y, side, f);
-			need = false;
+			if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(needmask));
+			base = __shfl_sync(FULL, base, leader);
+			if (need && !exhausted) {
+				item = base + __popc(needmask & ((1u << lane) - 1u));
+				if (item >= total) exhausted = true;
+				else {
+					leaf = (u32)(item / ppl);
+					const ulonglong2* lp = prep + 4 * (size_t)leaf;       // four 16-byte loads per playout
+					const ulonglong2 w0 = __ldg(lp), w1 = __ldg(lp + 1), b0 = __ldg(lp + 2), b1 = __ldg(lp + 3);
+					const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
+					const Side W = Side{w0.x, w0.y, w1.x, w1.y}, B = Side{b0.x, b0.y, b1.x, b1.y};
+					s.side = side; s.my = side ? B : W; s.en = side ? W : B;
+					s.ply = 0; s.rq = 0xffffffffu; s.chk_en = true; s.chk_my = true;
+					need = false;
+				}
+			}
 		}
-		const int o = fsim_step(s, rnd, key, first_id + item, max_plies, f);
+		if (__all_sync(FULL, exhausted)) break;
+		const int o = wstep(s, !exhausted, rnd, key, first_id + item, max_plies, f, smem + FAST_SQ_OFF);
 		if (o >= 0) {
 			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
 			my_plies += s.ply; my_playouts += 1;
 			need = true;
 		}
 	}
-	__syncwarp();
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1) {
-		my_plies += __shfl_xor_sync(0xffffffffu, my_plies, d);
-		my_playouts += __shfl_xor_sync(0xffffffffu, my_playouts, d);
+		my_plies += __shfl_xor_sync(FULL, my_plies, d);
+		my_playouts += __shfl_xor_sync(FULL, my_playouts, d);
 	}
 	if (lane == 0) { atomicAdd((unsigned long long*)stats, my_playouts); atomicAdd((unsigned long long*)stats + 1, my_plies); }
 }
@@ -213,6 +327,9 @@ cudaError_t loa_fast_prepare()
 	return cudaFuncSetAttribute(k_playout_trace_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
 }
 static int fast_grid(uint32_t n, int threads, int sms) { const int need = (int)((n + threads - 1) / threads); return need < sms ? (need ? need : 1) : sms; }
+
+void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, cudaStream_t st)
+{ if (n) k_prepare_leaves<<<(n + 127) / 128, 128, 0, st>>>((const ulonglong2*)d_boards, n, (ulonglong2*)d_prep); }
 
 void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
                              uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
