@@ -73,6 +73,11 @@ def lib():
         L.gai_loa_rollout_device.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp, _vp]
         L.gai_loa_playout_trace.argtypes = [_vp, _vp, _u32, _u32, _u64, _u64, _vp, _vp, _vp]
         L.gai_loa_gen_reachable.argtypes = [_vp, _u32, _u64, _u32, _vp, _vp, _vp]
+        L.gai_pan_movegen.argtypes = [_vp, _vp, _u32, _i32, _vp, _vp]
+        L.gai_pan_apply.argtypes = [_vp, _vp, _vp, _u32, _i32, _vp]
+        L.gai_pan_terminal.argtypes = [_vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]
+        L.gai_pan_rollout.argtypes = [_vp, _vp, _u32, _i32, _u32, _u32, _i32, _u64, _u64, _vp, _vp]
+        L.gai_pan_playout_trace.argtypes = [_vp, _vp, _u32, _i32, _u32, _i32, _u64, _u64, _vp, _vp, _vp, _vp]
         L.gai_dev_alloc.argtypes = [_vp, _u64, ctypes.POINTER(_vp)]
         L.gai_dev_free.argtypes = [_vp, _vp]
         L.gai_memcpy_h2d.argtypes = [_vp, _vp, _vp, _u64]
@@ -221,6 +226,47 @@ class GpuRollout:
         s = np.zeros((n, 3), np.uint64) if host else None
         self._ck(self.L.gai_loa_gen_reachable(self.h, n, key, max_k, d_boards, d_stm, s.ctypes.data if host else None))
         return s
+
+    # -- Pan (determinized) ---------------------------------------------------------------------
+    @staticmethod
+    def _pstates(states):
+        s = np.ascontiguousarray(states, dtype=np.uint64)
+        if s.ndim != 2 or s.shape[1] != 5:
+            raise ValueError("Pan states must have shape (n, 5): the reference's raw 40-byte GameState")
+        return s
+
+    def pan_movegen(self, num_players, states):
+        s = self._pstates(states); n = s.shape[0]
+        c = np.zeros(n, np.uint8); m = np.zeros((n, 16), np.uint64)
+        self._ck(self.L.gai_pan_movegen(self.h, s.ctypes.data, n, num_players, c.ctypes.data, m.ctypes.data))
+        return c, m
+
+    def pan_apply(self, num_players, states, moves):
+        s = self._pstates(states); n = s.shape[0]
+        mv = np.ascontiguousarray(moves, dtype=np.uint64); o = np.zeros((n, 5), np.uint64)
+        self._ck(self.L.gai_pan_apply(self.h, s.ctypes.data, mv.ctypes.data, n, num_players, o.ctypes.data))
+        return o
+
+    def pan_terminal(self, num_players, states):
+        s = self._pstates(states); n = s.shape[0]
+        t = np.zeros(n, np.uint8); sc = np.zeros((n, 4), np.int32); e0 = np.zeros((n, 4), np.int32); e1 = np.zeros((n, 4), np.int32)
+        self._ck(self.L.gai_pan_terminal(self.h, s.ctypes.data, n, num_players, t.ctypes.data, sc.ctypes.data, e0.ctypes.data, e1.ctypes.data))
+        return t, sc, e0, e1
+
+    def pan_rollout(self, num_players, states, playouts_per_leaf=1, max_plies=50, eval_kind=1, key=0x10A5EED, first_id=0):
+        """-> (res (n,12) uint32: losses[4], eval_sum[4], capped, pad[3]; stats dict)"""
+        s = self._pstates(states); n = s.shape[0]
+        r = np.zeros((n, 12), np.uint32); st = RolloutStats()
+        self._ck(self.L.gai_pan_rollout(self.h, s.ctypes.data, n, num_players, playouts_per_leaf, max_plies, eval_kind, key, first_id,
+                                        r.ctypes.data, ctypes.byref(st)))
+        return r, _stats(st)
+
+    def pan_playout_trace(self, num_players, states, max_plies=50, eval_kind=1, key=0x10A5EED, first_id=0):
+        s = self._pstates(states); n = s.shape[0]
+        c = np.zeros(n, np.uint8); pl = np.zeros(n, np.uint32); v = np.zeros((n, 4), np.int32); f = np.zeros((n, 5), np.uint64)
+        self._ck(self.L.gai_pan_playout_trace(self.h, s.ctypes.data, n, num_players, max_plies, eval_kind, key, first_id,
+                                              c.ctypes.data, pl.ctypes.data, v.ctypes.data, f.ctypes.data))
+        return c, pl, v, f
 
     # -- device memory ----------------------------------------------------------------------------
     def dev_alloc(self, nbytes):

@@ -454,6 +454,149 @@ int gai_loa_gen_reachable(gai_ctx* ctx, uint32_t n, uint64_t key, uint32_t max_k
 	return GAI_OK;
 }
 
+// ---- Pan ---------------------------------------------------------------------------------------------
+static int pan_check_np(gai_ctx* ctx, int np)
+{
+	if (np < 2 || np > 4) return fail(ctx, GAI_ERR_INVALID, "num_players must be 2, 3 or 4");
+	return GAI_OK;
+}
+static int pan_bad(gai_ctx* ctx, uint32_t bad)
+{
+	if (bad) return fail(ctx, GAI_ERR_INVALID, "Pan state with fuzzy (01/10) cards: the GPU path needs a determinized deal (every card 00 or 11)");
+	return GAI_OK;
+}
+#define PAN_BAD_PTR ((uint32_t*)((char*)ctx->d_misc.p + 48))
+
+int gai_pan_movegen(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int np, uint8_t* counts, gai_pan_move* moves)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	int r = pan_check_np(ctx, np); if (r) return r;
+	if (n == 0) return GAI_OK;
+	if (!states || !counts || !moves) return fail(ctx, GAI_ERR_INVALID, "gai_pan_movegen: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * 40, mb = (size_t)n * GAI_PAN_MAX_MOVES * 8;
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, mb, false); EN(ctx->d_misc, 64, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->d_out2.p, 0, mb, ctx->stream));
+	CU(cudaMemsetAsync(PAN_BAD_PTR, 0, 4, ctx->stream));
+	launch_pan_movegen(ctx->d_in.p, n, np, (uint8_t*)ctx->d_out.p, (uint64_t*)ctx->d_out2.p, PAN_BAD_PTR, ctx->stream);
+	LAUNCHED("k_pan_movegen");
+	uint32_t bad = 0;
+	CU(cudaMemcpyAsync(counts, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(moves, ctx->d_out2.p, mb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(&bad, PAN_BAD_PTR, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return pan_bad(ctx, bad);
+}
+
+int gai_pan_apply(gai_ctx* ctx, const gai_pan_state* states, const gai_pan_move* mv, uint32_t n, int np, gai_pan_state* out)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	int r = pan_check_np(ctx, np); if (r) return r;
+	if (n == 0) return GAI_OK;
+	if (!states || !mv || !out) return fail(ctx, GAI_ERR_INVALID, "gai_pan_apply: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * 40;
+	EN(ctx->d_in, sb, false); EN(ctx->d_in2, (size_t)n * 8, false); EN(ctx->d_out, sb, false); EN(ctx->d_misc, 64, false);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_in2.p, mv, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(PAN_BAD_PTR, 0, 4, ctx->stream));
+	launch_pan_apply(ctx->d_in.p, (const uint64_t*)ctx->d_in2.p, n, np, ctx->d_out.p, PAN_BAD_PTR, ctx->stream);
+	LAUNCHED("k_pan_apply");
+	uint32_t bad = 0;
+	CU(cudaMemcpyAsync(out, ctx->d_out.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(&bad, PAN_BAD_PTR, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return pan_bad(ctx, bad);
+}
+
+int gai_pan_terminal(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int np, uint8_t* terminal,
+                     int32_t* score, int32_t* ev0, int32_t* ev1)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	int r = pan_check_np(ctx, np); if (r) return r;
+	if (n == 0) return GAI_OK;
+	if (!states || !terminal || !score || !ev0 || !ev1) return fail(ctx, GAI_ERR_INVALID, "gai_pan_terminal: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * 40, vb = (size_t)n * 16;
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, 3 * vb, false); EN(ctx->d_misc, 64, false);
+	int* d_v = (int*)ctx->d_out2.p;
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(PAN_BAD_PTR, 0, 4, ctx->stream));
+	launch_pan_terminal(ctx->d_in.p, n, np, (uint8_t*)ctx->d_out.p, d_v, d_v + 4 * (size_t)n, d_v + 8 * (size_t)n, PAN_BAD_PTR, ctx->stream);
+	LAUNCHED("k_pan_terminal");
+	uint32_t bad = 0;
+	CU(cudaMemcpyAsync(terminal, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(score, d_v, vb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(ev0, d_v + 4 * (size_t)n, vb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(ev1, d_v + 8 * (size_t)n, vb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(&bad, PAN_BAD_PTR, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return pan_bad(ctx, bad);
+}
+
+int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves, int np, uint32_t ppl,
+                    uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id, gai_pan_result* out, gai_rollout_stats* stats)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (stats) memset(stats, 0, sizeof *stats);
+	int r = pan_check_np(ctx, np); if (r) return r;
+	if (n_leaves == 0) return GAI_OK;
+	if (!leaves || !out) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout: NULL buffer");
+	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout: playouts_per_leaf must be >= 1");
+	if (eval_kind != 0 && eval_kind != 1) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout: eval_kind must be 0 (num_cards) or 1 (num_cards_weighted)");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n_leaves * 40, rb = (size_t)n_leaves * sizeof(gai_pan_result);
+	EN(ctx->h_in, sb, true); EN(ctx->h_out, rb, true);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, rb, false); EN(ctx->d_misc, 64, false);
+	memcpy(ctx->h_in.p, leaves, sb);
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
+	CU(cudaMemsetAsync(ctx->d_out.p, 0, rb, ctx->stream));
+	const uint64_t total = (uint64_t)n_leaves * ppl;
+	int blocks = ctx->prop.multiProcessorCount * 8;
+	if ((total + 255) / 256 < (uint64_t)blocks) blocks = (int)((total + 255) / 256);
+	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	launch_pan_rollout(ctx->d_in.p, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, (uint32_t*)ctx->d_out.p,
+	                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2, PAN_BAD_PTR, blocks, ctx->stream);
+	LAUNCHED("k_pan_rollout");
+	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+	uint32_t bad = 0;
+	CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(&bad, PAN_BAD_PTR, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	memcpy(out, ctx->h_out.p, rb);
+	r = pan_bad(ctx, bad); if (r) return r;
+	return fill_stats(ctx, stats, true);
+}
+
+int gai_pan_playout_trace(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int np, uint32_t max_plies, int eval_kind,
+                          uint64_t key, uint64_t first_id, uint8_t* code, uint32_t* plies, int32_t* value, gai_pan_state* final_states)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	int r = pan_check_np(ctx, np); if (r) return r;
+	if (n == 0) return GAI_OK;
+	if (!states || !code || !plies || !value || !final_states) return fail(ctx, GAI_ERR_INVALID, "gai_pan_playout_trace: NULL buffer");
+	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n * 40;
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 20, false); EN(ctx->d_out3, sb, false); EN(ctx->d_misc, 64, false);
+	uint32_t* d_pl = (uint32_t*)ctx->d_out2.p; int* d_val = (int*)(d_pl + n);
+	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(PAN_BAD_PTR, 0, 4, ctx->stream));
+	launch_pan_playout_trace(ctx->d_in.p, n, np, max_plies, eval_kind, key, first_id, (uint8_t*)ctx->d_out.p, d_pl, d_val, ctx->d_out3.p, PAN_BAD_PTR, ctx->stream);
+	LAUNCHED("k_pan_playout_trace");
+	uint32_t bad = 0;
+	CU(cudaMemcpyAsync(code, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(plies, d_pl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(value, d_val, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(final_states, ctx->d_out3.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(&bad, PAN_BAD_PTR, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return pan_bad(ctx, bad);
+}
+
 // ---- device memory helpers -------------------------------------------------------------------------
 int gai_dev_alloc(gai_ctx* ctx, uint64_t bytes, void** d_ptr)
 {

@@ -30,3 +30,12 @@ void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n
 void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uint32_t n, uint64_t* d_hash, uint32_t* d_bad, int sms, cudaStream_t st);
 void launch_loa_playout_trace_fast(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
                                    uint8_t* d_outcome, uint32_t* d_plies, void* d_final, int sms, cudaStream_t st);
+
+// Pan (determinized) -- pan_kernels.cu
+void launch_pan_movegen(const void* d_states, uint32_t n, int np, uint8_t* d_counts, uint64_t* d_moves, uint32_t* d_bad, cudaStream_t st);
+void launch_pan_apply(const void* d_states, const uint64_t* d_mv, uint32_t n, int np, void* d_out, uint32_t* d_bad, cudaStream_t st);
+void launch_pan_terminal(const void* d_states, uint32_t n, int np, uint8_t* d_term, int* d_score, int* d_ev0, int* d_ev1, uint32_t* d_bad, cudaStream_t st);
+void launch_pan_playout_trace(const void* d_states, uint32_t n, int np, uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id,
+                              uint8_t* d_code, uint32_t* d_plies, int* d_value, void* d_final, uint32_t* d_bad, cudaStream_t st);
+void launch_pan_rollout(const void* d_states, uint32_t n_leaves, int np, uint32_t ppl, uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id,
+                        uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter, uint32_t* d_bad, int blocks, cudaStream_t st);

@@ -121,6 +121,40 @@ int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n,
                           uint64_t philox_key, uint64_t first_playout_id,
                           uint8_t* outcome, uint32_t* plies, gai_loa_state* final_states);
 
+/* ---- Pan ("Gra w Pana"), determinized rollouts (config 5) ------------------------------------ */
+/* GraWPanaZasadyV2.cpp:22-40 `struct GameState` as raw words, 40 bytes: w[0] = stack:48 | current_player:3 << 48 |
+ * is_terminal:1 << 51 ; w[1+p] = count:4 | cards:48 << 4 (Hand, :16-20).  Card c = rank*4 + suit at bits 2c..2c+1.
+ * The GPU path plays DETERMINIZED deals: every card field must be 00 or 11 (complete information); a state with
+ * fuzzy cards (01 / 10, CreatePlayerKnownState :214-243) is rejected with GAI_ERR_INVALID -- sample a deal first. */
+typedef struct gai_pan_state { uint64_t w[5]; } gai_pan_state;
+/* GraWPanaZasadyV2.cpp:42-49 `struct Move` raw: cards:48 | count:3 << 48 | operation:3 << 51 | probability:2 << 54 */
+typedef struct gai_pan_move { uint64_t w; } gai_pan_move;
+#define GAI_PAN_MAX_MOVES 16
+#define GAI_PAN_EVAL_NUM_CARDS 0            /* CreateEvalFunction("num_cards"), :255-261 */
+#define GAI_PAN_EVAL_NUM_CARDS_WEIGHTED 1   /* CreateEvalFunction("num_cards_weighted"), :285-300 */
+/* Per-leaf playout outcomes.  Terminal playouts: losses[p] counts playouts that left player p holding cards (Score
+ * :347-356 gives 100/(N-1) to everyone else).  Playouts stopped by the ply cap (MCTSConfig::MaxPlayoutDepth,
+ * playout_depth=50 in run_config.xml) are evaluated like MC::Player does (MCTSPlayer.cpp:486-488): eval_sum[p] adds
+ * the eval function's value for player p, capped counts them. */
+typedef struct gai_pan_result { uint32_t losses[4]; uint32_t eval_sum[4]; uint32_t capped; uint32_t reserved[3]; } gai_pan_result;
+
+/* IGameRules::GetPlayerLegalMoves (GraWPanaZasadyV2.cpp:409-475): moves[i*16 + k] = k-th move of the current player */
+int gai_pan_movegen(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int num_players, uint8_t* counts, gai_pan_move* moves);
+/* IGameRules::ApplyMove (:560-569 -> :534-557, next player :510-518, terminal flag :339-346) */
+int gai_pan_apply(gai_ctx* ctx, const gai_pan_state* states, const gai_pan_move* mv, uint32_t n, int num_players, gai_pan_state* out);
+/* checkIfTerminal + Score (:339-363) + both eval functions (:255-311): score/eval arrays are n x 4 int32 */
+int gai_pan_terminal(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int num_players, uint8_t* terminal,
+                     int32_t* score, int32_t* eval_num_cards, int32_t* eval_num_cards_weighted);
+/* HOST buffers: per leaf (= one sampled deal) playouts_per_leaf uniformly random playouts (ids first_playout_id +
+ * i*playouts_per_leaf + j) until one player is left holding cards or max_plies moves were made. */
+int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves, int num_players, uint32_t playouts_per_leaf,
+                    uint32_t max_plies, int eval_kind, uint64_t philox_key, uint64_t first_playout_id,
+                    gai_pan_result* out, gai_rollout_stats* stats);
+/* single playouts with detail: code[i] = loser 0..3, or 4 for a capped playout; value = Score / eval at the end */
+int gai_pan_playout_trace(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int num_players, uint32_t max_plies, int eval_kind,
+                          uint64_t philox_key, uint64_t first_playout_id, uint8_t* code, uint32_t* plies, int32_t* value,
+                          gai_pan_state* final_states);
+
 /* ---- synthetic corpus -------------------------------------------------------- */
 /* "reachable" positions: state i = the position after k_i random plies from the opening
  * (LinesOfActionZasady.cpp:358-365), k_i = philox(key^GEN, i, 0) % max_k, moves drawn from stream

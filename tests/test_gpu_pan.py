@@ -1,0 +1,86 @@
+"""GPU parity for Pan (config 5): determinized rules and Philox-driven playouts, bit-exact against the oracle and
+against committed outputs of the reference itself, through the C ABI."""
+import numpy as np
+import pytest
+from pan_util import ut_vectors, ref_corpus, mkmb, case_state, move_fields, OPS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import pan
+    return pan.port()
+
+
+def test_reference_ut_vectors_on_gpu(gpu):
+    for case in ut_vectors()["movegen_cases"]:
+        if case.get("fuzzy"):
+            continue
+        cnt, mv = gpu.pan_movegen(case["players"], case_state(case)[None])
+        assert cnt[0] == len(case["moves"]), case["name"]
+        for k, e in enumerate(case["moves"]):
+            f = move_fields(mv[0, k])
+            assert f["op"] == OPS[e["op"]] and f["cards"] == mkmb(e["cards"]) and f["count"] == e["count"] and f["prob"] == 3
+
+
+def test_fuzzy_states_are_refused(gpu, po):
+    import gameai_b200 as g
+    view = po.player_known_state(3, po.gen_reachable(3, 1, 1, 10)[0], 0)
+    with pytest.raises(g.GaiError):
+        gpu.pan_movegen(3, view[None])
+    with pytest.raises(g.GaiError):
+        gpu.pan_rollout(3, view[None], 2)
+    with pytest.raises(g.GaiError):
+        gpu.pan_rollout(5, view[None], 2)
+
+
+@pytest.mark.parametrize("npl", [2, 3, 4])
+def test_committed_reference_corpus_on_gpu(gpu, npl):
+    G = ref_corpus(); k = "p%d_" % npl
+    S = G[k + "states"]
+    c, m = gpu.pan_movegen(npl, S)
+    assert (c == G[k + "counts"]).all() and (m == G[k + "moves"]).all()
+    assert (gpu.pan_apply(npl, S, G[k + "pick"]) == G[k + "applied"]).all()
+    t, sc, e0, e1 = gpu.pan_terminal(npl, S)
+    assert (t == G[k + "terminal"]).all() and (sc == G[k + "score"]).all() and (e0 == G[k + "eval0"]).all() and (e1 == G[k + "eval1"]).all()
+    for tag, cap, ek in (("cap50w", 50, 1), ("cap50n", 50, 0), ("full", 100000, 1)):
+        code, pl, v, f = gpu.pan_playout_trace(npl, S[:400], cap, ek, int(G["seed"]), 500)
+        assert (code == G[k + tag + "_code"]).all() and (pl == G[k + tag + "_plies"]).all()
+        assert (v == G[k + tag + "_value"]).all() and (f == G[k + tag + "_final"]).all()
+
+
+@pytest.mark.parametrize("npl", [2, 3, 4])
+def test_rules_sweep_vs_oracle(gpu, po, npl):
+    S = po.gen_reachable(npl, 100_000, 0xBEEF + npl, 150)
+    c, m = gpu.pan_movegen(npl, S); oc, om = po.movegen_batch(npl, S)
+    assert (c == oc).all() and (m == om).all()
+    pick = (np.arange(len(S)) * 2654435761 % np.maximum(c.astype(np.int64), 1)).astype(np.int64)
+    mv = m[np.arange(len(S)), pick]
+    assert (gpu.pan_apply(npl, S, mv) == po.apply_batch(npl, S, mv)).all()
+    a, b = gpu.pan_terminal(npl, S), po.terminal_batch(npl, S)
+    assert all((x == y).all() for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("npl,ppl,cap,ek", [(2, 4, 50, 1), (3, 3, 50, 1), (4, 2, 50, 0), (3, 2, 100000, 1), (2, 1, 0, 1), (4, 5, 7, 1)])
+def test_rollout_counts_vs_oracle(gpu, po, npl, ppl, cap, ek):
+    S = po.gen_reachable(npl, 3000, 99 + npl, 120)
+    r, st = gpu.pan_rollout(npl, S, ppl, cap, ek, 0xFACE, 1 << 33)
+    orr, oplies = po.playout_batch(npl, S, ppl, cap, ek, 0xFACE, 1 << 33)
+    assert (r == orr).all()
+    assert st["plies"] == oplies and st["playouts"] == len(S) * ppl
+    assert (r[:, :4].sum(axis=1) + r[:, 8] == ppl).all()
+
+
+def test_rollout_full_size_properties(gpu, po):
+    """65 536 sampled deals x 16 playouts (3 players, playout_depth 50 as in run_config.xml): every playout accounted
+    for, idempotent, and a strided oracle sample agrees."""
+    npl, n, ppl = 3, 65536, 16
+    S = po.gen_reachable(npl, n, 2024, 60)
+    r, st = gpu.pan_rollout(npl, S, ppl, 50, 1, 11, 0)
+    assert (r[:, :4].sum(axis=1) + r[:, 8] == ppl).all() and (r[:, 3] == 0).all()
+    r2, st2 = gpu.pan_rollout(npl, S, ppl, 50, 1, 11, 0)
+    assert (r == r2).all() and st2["plies"] == st["plies"]
+    for i in range(0, n, 1021):
+        orr, _ = po.playout_batch(npl, S[i:i + 1], ppl, 50, 1, 11, i * ppl)
+        assert (orr[0] == r[i]).all()
