@@ -1,0 +1,216 @@
+// game-ai_b200/host/game_launcher.cpp -- GameLauncher + GameController for Linux: XML config -> plugins -> games.
+//
+// Keeps the reference's plugin model (c++/GameLauncher/GameLauncher.cpp:99-220, c++/GameController/GameController.cpp:27-217):
+// the <game provider="..."> attribute names the rules plugin, each <player provider="..."> a player plugin; both are
+// shared objects exporting createGameRules / createPlayer (BOOST_DLL_ALIAS in the reference, extern "C" + dlsym here);
+// --p1..--p4 pick <player name=...> entries, extra "key=value" tokens override attributes (GameLauncher.cpp:119-129).
+// The match loop is the reference's: every round every player is asked for a move (the one not to move returns the
+// noop list), Next() advances, repeated states and the round limit abort the game (GameController.cpp:59-97).
+#include "gameai/GamePlayer.h"
+#include "gameai/GameRules.h"
+#include "gameai/random_generator.h"
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using gai::Config;
+
+// ---- tiny XML attribute reader: <tag a="v" b="v"> ... enough for run_config*.xml -------------------------
+struct Element { std::string tag; Config attrs; };
+static std::vector<Element> parse_xml(const std::string& text)
+{
+	std::vector<Element> out;
+	size_t i = 0;
+	while ((i = text.find('<', i)) != std::string::npos) {
+		size_t j = text.find('>', i);
+		if (j == std::string::npos) break;
+		std::string body = text.substr(i + 1, j - i - 1);
+		i = j + 1;
+		if (body.empty() || body[0] == '?' || body[0] == '!' || body[0] == '/') continue;
+		Element e; size_t k = 0;
+		while (k < body.size() && !isspace((unsigned char)body[k]) && body[k] != '/') ++k;
+		e.tag = body.substr(0, k);
+		while (k < body.size()) {
+			while (k < body.size() && (isspace((unsigned char)body[k]) || body[k] == '/')) ++k;
+			size_t eq = body.find('=', k);
+			if (eq == std::string::npos) break;
+			std::string key = body.substr(k, eq - k);
+			key.erase(std::remove_if(key.begin(), key.end(), [](char c) { return isspace((unsigned char)c); }), key.end());
+			size_t q1 = body.find('"', eq); if (q1 == std::string::npos) break;
+			size_t q2 = body.find('"', q1 + 1); if (q2 == std::string::npos) break;
+			e.attrs.attrs[key] = body.substr(q1 + 1, q2 - q1 - 1);
+			k = q2 + 1;
+		}
+		out.push_back(e);
+	}
+	return out;
+}
+
+struct Rng : IRandomGenerator {
+	std::mt19937 g;
+	explicit Rng(unsigned seed) : g(seed) {}
+	std::vector<int> generateUniform(int lo, int hi, int n) override { std::vector<int> v(n); std::uniform_int_distribution<int> d(lo, hi); for (auto& x : v) x = d(g); return v; }
+	void release() override { delete this; }
+};
+
+static void* load_plugin(const std::string& provider, const std::string& dir)
+{
+	std::string lower = provider; std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
+	for (const std::string& nm : { dir + "/lib" + provider + ".so", dir + "/lib" + lower + ".so", "lib" + provider + ".so", "lib" + lower + ".so" }) {
+		if (void* h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL)) return h;
+	}
+	std::fprintf(stderr, "cannot load plugin '%s': %s\n", provider.c_str(), dlerror());
+	return nullptr;
+}
+
+enum class SingleGameResult { Win = 0, RoundLimit = 1, StateLoop = 2 };
+
+// GameController.cpp:27-115
+static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlayer*>& players, GameState* state, int round_limit, int score[], int verbose, int* rounds_out)
+{
+	const int np = (int)players.size();
+	std::vector<GameState*> pks(np);
+	for (int i = 0; i < np; ++i) { pks[i] = rules->CreatePlayerKnownState(state, i); players[i]->startNewGame(pks[i]); }
+	std::set<std::string> seen;
+	SingleGameResult result = SingleGameResult::Win;
+	std::vector<MoveList*> moves(np);
+	int round = 0;
+	for (;;) {
+		for (int i = 0; i < np; ++i) moves[i] = players[i]->selectMove(pks[i]);
+		if (verbose) {
+			const int cp = rules->GetCurrentPlayer(state);
+			auto [mv, p] = rules->GetMoveFromList(moves[cp], 0); (void)p;
+			std::printf("round %d player %d (%s): %s\n", round, cp, players[cp]->getName().c_str(), rules->ToString(mv).c_str());
+		}
+		state = rules->Next(state, moves);
+		const std::string key = rules->ToString(state);
+		const bool loop = !seen.insert(key).second;
+		for (int i = 0; i < np; ++i) rules->UpdatePlayerKnownState(pks[i], state, moves);
+		for (int i = 0; i < np; ++i) rules->ReleaseMoveList(moves[i]);
+		++round;
+		if (loop) { result = SingleGameResult::StateLoop; break; }
+		if (round >= round_limit) { result = SingleGameResult::RoundLimit; break; }
+		if (rules->IsTerminal(state)) break;
+	}
+	rules->Score(state, score);
+	if (verbose) std::printf("final state:\n%s\n", rules->ToString(state).c_str());
+	for (int i = 0; i < np; ++i) {
+		const GameResult gr = result == SingleGameResult::Win ? (score[i] == 100 ? GameResult::Win : score[i] == 0 ? GameResult::Loose : GameResult::Draw)
+		                    : result == SingleGameResult::RoundLimit ? GameResult::AbortedByRoundLimit : GameResult::AbortedByStateLoop;
+		players[i]->endGame(score[i], gr);
+		rules->ReleaseGameState(pks[i]);
+	}
+	rules->ReleaseGameState(state);
+	*rounds_out = round;
+	return result;
+}
+
+int main(int argc, char** argv)
+{
+	std::string xml = "run_config_loa.xml", plugin_dir;
+	std::vector<std::string> pnames(4);
+	int num_games = -1, round_limit = -1, verbose = 0;
+	unsigned seed = 12345;
+	{	// plugins live next to the executable
+		std::string self = argv[0]; size_t sl = self.find_last_of('/'); plugin_dir = sl == std::string::npos ? "." : self.substr(0, sl);
+	}
+	for (int i = 1; i < argc; ++i) {
+		std::string a = argv[i];
+		auto next = [&]() -> std::string { return i + 1 < argc ? argv[++i] : ""; };
+		if (a == "--xml") xml = next();
+		else if (a == "--p1" || a == "--p2" || a == "--p3" || a == "--p4") pnames[a[3] - '1'] = next();
+		else if (a == "--ng") num_games = atoi(next().c_str());
+		else if (a == "--rl") round_limit = atoi(next().c_str());
+		else if (a == "--seed") seed = (unsigned)strtoul(next().c_str(), nullptr, 10);
+		else if (a == "--verbose" || a == "-v") verbose = 1;
+		else if (a == "--plugins") plugin_dir = next();
+		else if (a == "--help" || a == "-h") { std::printf("usage: GameLauncher --xml cfg.xml --p1 \"name [key=value ...]\" --p2 name [--ng N] [--rl N] [--seed S] [-v]\n"); return 0; }
+	}
+	std::ifstream f(xml);
+	if (!f) { std::fprintf(stderr, "cannot open %s\n", xml.c_str()); return 2; }
+	std::stringstream ss; ss << f.rdbuf();
+	auto elems = parse_xml(ss.str());
+	Config game; std::vector<Config> player_defs;
+	for (auto& e : elems) { if (e.tag == "game") game = e.attrs; else if (e.tag == "player") player_defs.push_back(e.attrs); }
+	if (num_games < 0) num_games = game.get_optional<int>("num_games").get_value_or(1);
+	if (round_limit < 0) round_limit = game.get_optional<int>("round_limit").get_value_or(300);
+
+	void* hr = load_plugin(game.get<std::string>("provider"), plugin_dir);
+	if (!hr) return 3;
+	auto create_rules = (CreateGameRules_t)dlsym(hr, "createGameRules");
+	if (!create_rules) { std::fprintf(stderr, "plugin lacks createGameRules\n"); return 3; }
+
+	// selectPlayerConfigs (GameLauncher.cpp:99-137): "--p1 'mcts key=value ...'"
+	std::vector<Config> pcfg;
+	for (auto& spec : pnames) {
+		if (spec.empty()) continue;
+		std::istringstream ts(spec); std::string name; ts >> name;
+		Config c; bool found = false;
+		for (auto& d : player_defs) if (d.get_optional<std::string>("name").get_value_or("") == name) { c = d; found = true; break; }
+		if (!found) { std::fprintf(stderr, "no <player name=\"%s\"> in %s\n", name.c_str(), xml.c_str()); return 2; }
+		std::string tok, full = name;
+		while (ts >> tok) { size_t eq = tok.find('='); if (eq != std::string::npos) { c.attrs[tok.substr(0, eq)] = tok.substr(eq + 1); full += "_" + tok; } }
+		c.attrs["fullname"] = full;
+		pcfg.push_back(c);
+	}
+	const int np = (int)pcfg.size();
+	if (np < 2) { std::fprintf(stderr, "need at least --p1 and --p2\n"); return 2; }
+
+	IGameRules* rules = create_rules(np);
+	Rng* rng = new Rng(seed);
+	std::vector<IGamePlayer*> players;
+	try {
+		for (int i = 0; i < np; ++i) {
+			pcfg[i].put("number_of_players", np);                                        // GameController.cpp:152-155
+			if (!pcfg[i].get_optional<unsigned>("random_seed")) pcfg[i].put("random_seed", seed + 1000u * (unsigned)(i + 1));
+			void* hp = load_plugin(pcfg[i].get<std::string>("provider"), plugin_dir);
+			if (!hp) return 3;
+			auto create_player = (CreatePlayer_t)dlsym(hp, "createPlayer");
+			if (!create_player) { std::fprintf(stderr, "plugin lacks createPlayer\n"); return 3; }
+			IGamePlayer* p = create_player(i, &pcfg[i]);
+			p->setGameRules(rules);
+			players.push_back(p);
+		}
+	} catch (const char* msg) { std::fprintf(stderr, "error: %s\n", msg); return 4; }
+
+	std::vector<double> pts(np, 0); std::vector<int> wins(np, 0), loses(np, 0);
+	int aborted = 0; long rounds_total = 0;
+	const auto t0 = std::chrono::steady_clock::now();
+	try {
+		for (int g = 0; g < num_games; ++g) {
+			int score[4] = { 0, 0, 0, 0 }, rounds = 0;
+			GameState* st = rules->CreateRandomInitialState(rng);
+			const SingleGameResult r = run_single_game(rules, players, st, round_limit, score, verbose, &rounds);
+			rounds_total += rounds;
+			if (r != SingleGameResult::Win) ++aborted;
+			for (int i = 0; i < np; ++i) { pts[i] += score[i]; if (r == SingleGameResult::Win) { if (score[i] == 100) ++wins[i]; else if (score[i] == 0) ++loses[i]; } }
+			std::printf("game %d: %s after %d rounds, score", g + 1, r == SingleGameResult::Win ? "finished" : r == SingleGameResult::RoundLimit ? "round limit" : "state loop", rounds);
+			for (int i = 0; i < np; ++i) std::printf(" %s=%d", players[i]->getName().c_str(), score[i]);
+			std::printf("\n"); std::fflush(stdout);
+		}
+	} catch (const char* msg) { std::fprintf(stderr, "error: %s\n", msg); return 4; }
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+	// results (the reference writes the same fields to results.xml: pN.pts / pN.win / pN.lose + player metrics, GameController.cpp:101-111,199)
+	std::printf("{\"games\": %d, \"aborted\": %d, \"rounds\": %ld, \"seconds\": %.3f, \"players\": [", num_games, aborted, rounds_total, secs);
+	for (int i = 0; i < np; ++i) {
+		std::printf("%s{\"name\": \"%s\", \"pts\": %.1f, \"win\": %d, \"lose\": %d, \"stats\": {", i ? ", " : "", players[i]->getName().c_str(), pts[i], wins[i], loses[i]);
+		bool first = true;
+		for (auto& kv : players[i]->getGameStats()) { std::printf("%s\"%s\": \"%s\"", first ? "" : ", ", kv.first.c_str(), metric_to_string(kv.second).c_str()); first = false; }
+		std::printf("}}");
+	}
+	std::printf("]}\n");
+	for (auto* p : players) p->release();
+	rules->Release();
+	rng->release();
+	return 0;
+}

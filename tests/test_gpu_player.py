@@ -1,0 +1,40 @@
+"""GPU, tier 3: the GPU-backed MCTS player through the reference-shaped plugin chain
+(GameLauncher -> createGameRules / createPlayer -> IGamePlayer::selectMove -> gai_loa_rollout)."""
+import json
+import os
+import subprocess
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LAUNCHER = os.path.join(ROOT, "game-ai_b200", "host", "GameLauncher")
+XML = os.path.join(ROOT, "run_config_loa.xml")
+
+
+def run(*args):
+    r = subprocess.run([LAUNCHER, "--xml", XML] + list(args), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_gpu_mcts_beats_random_and_shallow_alphabeta():
+    # win-rate tolerance: a uniformly random mover (or a 2-ply search with the rules' constant eval, which is
+    # what the reference's MinMaxAB sees on LOA) must lose essentially every game to 0.2 s of MCTS
+    res = run("--p1", "mcts move_time_limit=0.2", "--p2", "random", "--ng", "6", "--seed", "3")
+    assert res["players"][0]["win"] >= 5, res
+    stats = res["players"][0]["stats"]
+    assert float(stats["playouts_per_sec"]) > 1e5 and float(stats["gpu_batches"]) > 0
+    res = run("--p1", "ab3 search_depth=2", "--p2", "mcts move_time_limit=0.2", "--ng", "4", "--seed", "4")
+    assert res["players"][1]["win"] >= 3, res
+
+
+def test_fixed_simulation_budget_is_reproducible():
+    a = run("--p1", "mcts move_sim_limit=65536 random_seed=7 philox_seed=9", "--p2", "random", "--ng", "1", "--seed", "8")
+    b = run("--p1", "mcts move_sim_limit=65536 random_seed=7 philox_seed=9", "--p2", "random", "--ng", "1", "--seed", "8")
+    assert a["rounds"] == b["rounds"] and a["players"][0]["pts"] == b["players"][0]["pts"]
+
+
+def test_root_parallel_two_trees_one_process():
+    # two independent trees (two contexts; on a 1-GPU box both on device 0) merged at the root
+    res = run("--p1", "mcts move_time_limit=0.2 devices=0,0", "--p2", "random", "--ng", "2", "--seed", "5")
+    assert res["players"][0]["win"] == 2, res

@@ -1,0 +1,65 @@
+"""CPU tests of the host side above the C ABI: the LOA rules plugin (createGameRules), the launcher/controller and the
+CPU opponents.  The GPU-backed player must refuse to play without a GPU (no CPU fallback)."""
+import ctypes
+import json
+import os
+import subprocess
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "game-ai_b200", "host")
+LAUNCHER = os.path.join(HOST, "GameLauncher")
+XML = os.path.join(ROOT, "run_config_loa.xml")
+
+
+@pytest.fixture(scope="module")
+def hostrules():
+    L = ctypes.CDLL(os.path.join(HOST, "libLinesOfActionZasady.so"))
+    L.loa_host_movegen.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p]
+    L.loa_host_terminal_score.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    L.loa_host_next.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    return L
+
+
+def test_plugins_export_the_reference_entry_points():
+    for lib, sym in (("libLinesOfActionZasady.so", "createGameRules"), ("libgpumctsplayer.so", "createPlayer"), ("libSimpleStrategyPlayer.so", "createPlayer")):
+        L = ctypes.CDLL(os.path.join(HOST, lib))
+        assert hasattr(L, sym), (lib, sym)
+
+
+def test_host_rules_plugin_vs_oracle(hostrules, oracle):
+    S = np.concatenate([oracle.gen_reachable(1500, 3), oracle.gen_uniform(1500, 3)])
+    oc, om = oracle.movegen_batch(S); ot, osc = oracle.terminal_batch(S)
+    buf = (ctypes.c_uint8 * 256)(); sc = (ctypes.c_int * 2)(); out = (ctypes.c_uint64 * 3)()
+    for i, (w, b, cp) in enumerate(S.tolist()):
+        n = hostrules.loa_host_movegen(w, b, cp, buf)
+        assert n == oc[i] and [buf[k] for k in range(2 * n)] == om[i, :n].reshape(-1).tolist()
+        assert hostrules.loa_host_terminal_score(w, b, sc) == ot[i] and [sc[0], sc[1]] == osc[i].tolist()
+        if n:
+            f, t = om[i, i % n].tolist()
+            hostrules.loa_host_next(w, b, cp, f, t, out)                 # Next() = move of the mover + noop of the other
+            assert (out[0], out[1], out[2] & 1) == oracle.apply(w, b, cp, f, t)
+
+
+def run_launcher(*args):
+    r = subprocess.run([LAUNCHER, "--xml", XML] + list(args), capture_output=True, text=True, timeout=600)
+    return r
+
+
+def test_launcher_cpu_players_are_deterministic():
+    a = run_launcher("--p1", "random", "--p2", "ab3 search_depth=2", "--ng", "4", "--seed", "11")
+    b = run_launcher("--p1", "random", "--p2", "ab3 search_depth=2", "--ng", "4", "--seed", "11")
+    assert a.returncode == 0, a.stderr
+    ra, rb = json.loads(a.stdout.strip().splitlines()[-1]), json.loads(b.stdout.strip().splitlines()[-1])
+    assert ra["games"] == 4 and ra["players"][0]["name"] == "random" and ra["players"][1]["name"] == "ab3_search_depth=2"
+    assert [p["pts"] for p in ra["players"]] == [p["pts"] for p in rb["players"]] and ra["rounds"] == rb["rounds"]
+    assert ra["players"][1]["win"] >= 3                                   # a 2-ply search beats the random mover
+
+
+def test_gpu_player_refuses_to_play_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = run_launcher("--p1", "mcts", "--p2", "random", "--ng", "1")
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
