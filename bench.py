@@ -208,7 +208,9 @@ def main():
 
     # synthetic corpus, generated on the device straight into the rollout layout (resident in HBM)
     d_b = eng.dev_alloc(n * 16); d_s = eng.dev_alloc(((n + 31) // 32) * 4); d_o = eng.dev_alloc(n * 16)
-    corpus_key = SEED + rank                      # every rank plays its own shard
+    import importlib
+    plan = importlib.import_module("game-ai_b200.rootpar").shard_plan(rank, world, n, ppl, SEED)
+    corpus_key = plan["corpus_key"]               # every rank plays its own shard
     host_states = eng.gen_reachable(n, corpus_key, 300, d_boards=d_b, d_stm=d_s, host=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
@@ -218,7 +220,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    first_id = rank * n * ppl
+    first_id = plan["first_playout_id"]
     for _ in range(args.warmup):
         eng.rollout_device(d_b, d_s, n, d_o, ppl, MAX_PLIES, SEED, first_id)
     launches0 = eng.launch_count()
