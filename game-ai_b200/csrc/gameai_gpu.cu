@@ -102,16 +102,21 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
                     uint32_t max_plies, uint64_t key, uint64_t first_id, void* d_out)
 {
 	EN(ctx->d_misc, 64, false);
-	if (ctx->impl == 1) EN(ctx->d_prep, (size_t)n_leaves * 64, false);
+	// d_prep: [n x 64 B rotations][n x u32 order][n x u8 piece counts][64 x u32 histogram + cursors]
+	const size_t prep_b = (size_t)n_leaves * 64, ord_b = (size_t)n_leaves * 4, pc_b = ((size_t)n_leaves + 255) / 256 * 256;
+	if (ctx->impl == 1) EN(ctx->d_prep, prep_b + ord_b + pc_b + 256, false);
 	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
 	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 	if (ctx->impl == 1) {
 		// rotations of every leaf, once per batch (inside the timed region: it is part of the step)
-		launch_loa_prepare_leaves(d_boards, n_leaves, ctx->d_prep.p, ctx->stream);
-		LAUNCHED("k_prepare_leaves");
-		launch_loa_rollout_fast(ctx->d_lut, ctx->d_prep.p, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
+		char* pb = (char*)ctx->d_prep.p;
+		uint32_t* d_order = (uint32_t*)(pb + prep_b); uint8_t* d_pc = (uint8_t*)(pb + prep_b + ord_b); uint32_t* d_hist = (uint32_t*)(pb + prep_b + ord_b + pc_b);
+		CU(cudaMemsetAsync(d_hist, 0, 256, ctx->stream));
+		launch_loa_prepare_leaves(d_boards, n_leaves, pb, d_pc, d_hist, d_order, ctx->stream);
+		LAUNCHED("k_prepare_leaves"); ctx->launches += 1;      // + k_order_leaves
+		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
 		                        ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->stream);
 	} else

@@ -166,11 +166,24 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 // Leaf preparation: the four rotations of both colours, once per leaf (64 B = 4 x 16-byte vectors), so that a
 // lane that pulls a new playout issues four LDG.128 instead of rebuilding the rotations piece by piece while the
 // other 31 lanes of its warp wait (ncu: 6 % of all issued instructions at 1 active lane before this kernel existed).
-__global__ void k_prepare_leaves(const ulonglong2* __restrict__ boards, u32 n, ulonglong2* __restrict__ prep)
+//
+// Scheduling: the piece loop of the rollout kernel runs for the warp-wide MAXIMUM number of own pieces, so lanes that
+// hold late-game positions idle while a neighbour works through an opening position.  Leaves are therefore handed out in
+// order of DESCENDING piece count (counting sort: histogram here, scatter in k_order_leaves): at any moment every lane on
+// the GPU is refilled from the same piece-count bucket and older playouts have aged towards it.  The order changes which
+// lane runs a playout, never its result (playout id = leaf index * ppl + j).
+__global__ void k_prepare_leaves(const ulonglong2* __restrict__ boards, u32 n, ulonglong2* __restrict__ prep,
+                                 uint8_t* __restrict__ pcount, u32* __restrict__ hist)
 {
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const ulonglong2 bd = boards[i];
+	{
+		u32 pc = (u32)(__popcll(bd.x) + __popcll(bd.y));
+		pc = pc > 31u ? 31u : pc;
+		pcount[i] = (uint8_t)pc;
+		atomicAdd(hist + pc, 1u);
+	}
 	const Side w = make_side(bd.x, c_sqt.w), b = make_side(bd.y, c_sqt.w);
 	prep[4 * (size_t)i + 0] = make_ulonglong2(w.R, w.C);
 	prep[4 * (size_t)i + 1] = make_ulonglong2(w.D1, w.D2);
@@ -178,8 +191,19 @@ __global__ void k_prepare_leaves(const ulonglong2* __restrict__ boards, u32 n, u
 	prep[4 * (size_t)i + 3] = make_ulonglong2(b.D1, b.D2);
 }
 
+// hist[0..31] = leaves per piece count, hist[32..63] = scatter cursors (zeroed by the host before k_prepare_leaves)
+__global__ void k_order_leaves(const uint8_t* __restrict__ pcount, u32 n, u32* __restrict__ hist, u32* __restrict__ order)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u32 pc = pcount[i];
+	u32 off = 0;
+	for (u32 q = pc + 1; q < 32; ++q) off += hist[q];            // buckets with more pieces come first
+	order[off + atomicAdd(hist + 32 + pc, 1u)] = i;
+}
+
 __global__ void __launch_bounds__(1024, 1)
-k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm,
+k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm, const u32* __restrict__ order,
                u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
                u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
 {
@@ -189,7 +213,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 	const u64 total = (u64)n_leaves * ppl;
 	const u32 lane = threadIdx.x & 31u;
 	FastSim s; gai::Philox4 rnd;
-	u64 item = 0; u32 leaf = 0;
+	u64 item = 0, pid = 0; u32 leaf = 0;
 	bool need = true, exhausted = false;
 	u64 my_plies = 0, my_playouts = 0;
 	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
@@ -207,7 +231,9 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 				item = base + __popc(needmask & ((1u << lane) - 1u));
 				if (item >= total) exhausted = true;
 				else {
-					leaf = (u32)(item / ppl);
+					const u32 slot = (u32)(item / ppl);
+					leaf = __ldg(order + slot);
+					pid = first_id + (u64)leaf * ppl + (item - (u64)slot * ppl);       // identity = (leaf, playout), not the schedule
 					const ulonglong2* lp = prep + 4 * (size_t)leaf;       // four 16-byte loads per playout
 					const ulonglong2 w0 = __ldg(lp), w1 = __ldg(lp + 1), b0 = __ldg(lp + 2), b1 = __ldg(lp + 3);
 					const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
@@ -219,7 +245,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 			}
 		}
 		if (__all_sync(FULL, exhausted)) break;
-		const int o = wstep(s, !exhausted, rnd, key, first_id + item, max_plies, f, smem + FAST_SQ_OFF);
+		const int o = wstep(s, !exhausted, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
 		if (o >= 0) {
 			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
 			my_plies += s.ply; my_playouts += 1;
@@ -328,16 +354,20 @@ cudaError_t loa_fast_prepare()
 }
 static int fast_grid(uint32_t n, int threads, int sms) { const int need = (int)((n + threads - 1) / threads); return need < sms ? (need ? need : 1) : sms; }
 
-void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, cudaStream_t st)
-{ if (n) k_prepare_leaves<<<(n + 127) / 128, 128, 0, st>>>((const ulonglong2*)d_boards, n, (ulonglong2*)d_prep); }
+void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, uint8_t* d_pcount, uint32_t* d_hist, uint32_t* d_order, cudaStream_t st)
+{
+	if (!n) return;
+	k_prepare_leaves<<<(n + 127) / 128, 128, 0, st>>>((const ulonglong2*)d_boards, n, (ulonglong2*)d_prep, d_pcount, d_hist);
+	k_order_leaves<<<(n + 255) / 256, 256, 0, st>>>(d_pcount, n, d_hist, d_order);
+}
 
-void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, const uint32_t* d_order, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
                              uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
                              int threads, int sms, cudaStream_t st)
 {
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	const int blocks = fast_grid(total > 0xffffffffull ? 0xffffffffu : (uint32_t)total, threads, sms);
-	k_rollout_fast<<<blocks, threads, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, n_leaves, ppl, max_plies,
+	k_rollout_fast<<<blocks, threads, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies,
 	                                                          key, first_id, d_out, (u64*)d_stats, d_counter);
 }
 void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
