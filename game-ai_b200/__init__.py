@@ -157,7 +157,7 @@ class GpuRollout:
         self._ck(self.L.gai_set_launch_config(self.h, threads_per_block, blocks_per_sm))
 
     def set_rules_impl(self, impl):
-        """0 = bitboard baseline kernels, 1 = rotated boards + line LUT (default)."""
+        """0 = bitboard baseline kernels, 1 = rotated boards + line LUT per piece, 2 = static line sweep."""
         self._ck(self.L.gai_set_rules_impl(self.h, impl))
 
     def sync(self):

@@ -104,12 +104,12 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
 	EN(ctx->d_misc, 64, false);
 	// d_prep: [n x 64 B rotations][n x u32 order][n x u8 piece counts][64 x u32 histogram + cursors]
 	const size_t prep_b = (size_t)n_leaves * 64, ord_b = (size_t)n_leaves * 4, pc_b = ((size_t)n_leaves + 255) / 256 * 256;
-	if (ctx->impl == 1) EN(ctx->d_prep, prep_b + ord_b + pc_b + 256, false);
+	if (ctx->impl >= 1) EN(ctx->d_prep, prep_b + ord_b + pc_b + 256, false);
 	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
 	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-	if (ctx->impl == 1) {
+	if (ctx->impl >= 1) {
 		// rotations of every leaf, once per batch (inside the timed region: it is part of the step)
 		char* pb = (char*)ctx->d_prep.p;
 		uint32_t* d_order = (uint32_t*)(pb + prep_b); uint8_t* d_pc = (uint8_t*)(pb + prep_b + ord_b); uint32_t* d_hist = (uint32_t*)(pb + prep_b + ord_b + pc_b);
@@ -118,7 +118,7 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
 		LAUNCHED("k_prepare_leaves"); ctx->launches += 1;      // + k_order_leaves
 		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
-		                        ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->stream);
+		                        ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2, ctx->stream);
 	} else
 		launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
@@ -249,7 +249,7 @@ uint64_t gai_launch_count(const gai_ctx* ctx) { return ctx ? ctx->launches : 0; 
 int gai_set_rules_impl(gai_ctx* ctx, int impl)
 {
 	if (!ctx) return GAI_ERR_INVALID;
-	if (impl != 0 && impl != 1) return fail(ctx, GAI_ERR_INVALID, "rules impl must be 0 (bitboard baseline) or 1 (rotated boards + line LUT)");
+	if (impl < 0 || impl > 2) return fail(ctx, GAI_ERR_INVALID, "rules impl must be 0 (bitboard baseline), 1 (rotated boards + line LUT, per piece) or 2 (static line sweep)");
 	ctx->impl = impl;
 	return GAI_OK;
 }
@@ -265,7 +265,8 @@ int gai_loa_movegen(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, mb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemsetAsync(ctx->d_out2.p, 0, mb, ctx->stream));
-	if (ctx->impl == 1) launch_loa_movegen_fast(ctx->d_lut, ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->prop.multiProcessorCount, ctx->stream);
+	if (ctx->impl == 2) launch_loa_movegen_sweep(ctx->d_lut, ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->prop.multiProcessorCount, ctx->stream);
+	else if (ctx->impl == 1) launch_loa_movegen_fast(ctx->d_lut, ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->prop.multiProcessorCount, ctx->stream);
 	else launch_loa_movegen(ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, (uint8_t*)ctx->d_out2.p, ctx->stream);
 	LAUNCHED("k_movegen");
 	CU(cudaMemcpyAsync(counts, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -318,14 +319,14 @@ int gai_loa_successor_hash(gai_ctx* ctx, const gai_loa_state* states, uint32_t n
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, (size_t)n * 8, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
 	uint32_t bad = 0;
-	if (ctx->impl == 1) {
+	if (ctx->impl >= 1) {
 		EN(ctx->d_misc, 64, false);
 		CU(cudaMemsetAsync((char*)ctx->d_misc.p + 32, 0, 4, ctx->stream));
 		launch_loa_successor_hash_fast(ctx->d_lut, ctx->d_in.p, n, (uint64_t*)ctx->d_out.p, (uint32_t*)((char*)ctx->d_misc.p + 32), ctx->prop.multiProcessorCount, ctx->stream);
 	} else launch_loa_successor_hash(ctx->d_in.p, n, (uint64_t*)ctx->d_out.p, ctx->stream);
 	LAUNCHED("k_successor_hash");
 	CU(cudaMemcpyAsync(hash, ctx->d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	if (ctx->impl == 1) CU(cudaMemcpyAsync(&bad, (char*)ctx->d_misc.p + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->impl >= 1) CU(cudaMemcpyAsync(&bad, (char*)ctx->d_misc.p + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	if (bad) return fail(ctx, GAI_ERR_CUDA, "rotated boards diverged from the plain bitboard after apply (internal consistency check)");
 	return GAI_OK;
@@ -426,7 +427,7 @@ int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n,
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 4, false); EN(ctx->d_out3, sb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
-	if (ctx->impl == 1)
+	if (ctx->impl >= 1)
 		launch_loa_playout_trace_fast(ctx->d_lut, ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
 		                              (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->prop.multiProcessorCount, ctx->stream);
 	else

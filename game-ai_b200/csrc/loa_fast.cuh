@@ -7,11 +7,13 @@
 //  * each colour is held in four 64-bit "rotated" boards in registers, so that every line through a square is
 //    ONE BYTE of one register pair:
 //        R  : byte = row r          cell = column c           (the plain bitboard, LinesOfActionZasady.cpp:43)
-//        C  : byte = column c       cell = 7 - r              (transposed, rows reversed)
+//        C  : byte = column c       cell = row r              (transposed)
 //        D1 : byte = (r - c) & 7    cell = column c           ("left" diagonal A1->H8, :93-113)
 //        D2 : byte = (r + c) & 7    cell = row r              ("right" diagonal H1->A8, :114-135)
-//    The cell orientation is chosen so that in all four the reference's FIRST direction of the line
-//    (W, N, SW, SE -- :194-223) is "towards lower cells" and the second (E, S, NE, NW) "towards higher cells".
+//    In R, D1 and D2 the reference's FIRST direction of the line (W, SW, SE -- :194-223) is "towards lower cells" and
+//    the second (E, NE, NW) "towards higher cells"; in C it is the other way round (N = higher row comes first), the
+//    two bits of a C field are swapped when a piece's move mask is assembled.  C, D2 and (after a rotation) D1 all
+//    index their cells by ROW, which is what the static sweep in loa_sweep.cuh relies on.
 //    A D1/D2 byte holds two complementary diagonals (lengths k and 8-k); the cells of the other diagonal are
 //    presented to the LUT as "phantom" cells.
 //  * one table LUT[(o8, e8)] (own / enemy occupancy of the 8 cells) -> 16 bits, 2 per cell:
@@ -53,7 +55,7 @@ __host__ __device__ inline uint16_t lut_entry(u32 o, u32 e)
 }
 
 // rotated-board bit positions of square s = 8r + c
-__host__ __device__ constexpr int pos_c(int s)  { return 8 * (s & 7) + (7 - (s >> 3)); }
+__host__ __device__ constexpr int pos_c(int s)  { return 8 * (s & 7) + (s >> 3); }
 __host__ __device__ constexpr int pos_d1(int s) { return 8 * (((s >> 3) - (s & 7)) & 7) + (s & 7); }
 __host__ __device__ constexpr int pos_d2(int s) { return 8 * (((s >> 3) + (s & 7)) & 7) + (s >> 3); }
 // phantom cells of the D1 / D2 byte seen from square s (cells that belong to the complementary diagonal)
@@ -119,7 +121,8 @@ __device__ __forceinline__ u32 piece_moves_fast(const Side& my, const Side& en, 
 	const u32 v1 = lut_lookup(lut, byte_of(my.D1, k1), byte_of(en.D1, k1), ph1);
 	const u32 v2 = lut_lookup(lut, byte_of(my.D2, k2), byte_of(en.D2, k2), ph2);
 	const u32 xR = (vR >> (2u * c)) & 3u;            // W, E
-	const u32 xC = (vC >> (14u - 2u * r)) & 3u;      // N, S
+	const u32 xCs = (vC >> (2u * r)) & 3u;           // bit0 = S (lower row), bit1 = N
+	const u32 xC = ((xCs >> 1) | (xCs << 1)) & 3u;   // N, S
 	const u32 x1 = (v1 >> (2u * c)) & 3u;            // SW, NE
 	const u32 x2 = (v2 >> (2u * r)) & 3u;            // SE, NW
 	return xR + xC * 4u + x1 * 16u + x2 * 64u;

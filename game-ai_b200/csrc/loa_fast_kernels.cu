@@ -1,6 +1,7 @@
 // game-ai_b200/csrc/loa_fast_kernels.cu -- rollout / sweep kernels on the "rotated boards + line LUT" rules.
 // One CTA per SM (the 129 KB line LUT lives in shared memory), persistent, one playout per thread.
 #include "loa_fast.cuh"
+#include "loa_sweep.cuh"
 #include "loa_sim.cuh"
 #include "kernels.h"
 
@@ -102,6 +103,7 @@ __device__ __forceinline__ bool wconnected(u64 b, bool want)
 
 // One ply for every lane with alive == true.  Returns the outcome code for lanes whose playout ended in this
 // step, -1 otherwise (also for lanes that were not alive).
+template <bool SWEEP>
 __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies, const FastSmem& f,
                                      unsigned char* __restrict__ sq_scratch)
 {
@@ -115,6 +117,32 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 	if (term) { const bool wc = s.side ? c_en : c_my, bc = s.side ? c_my : c_en; result = outcome_of(wc, bc); }
 	if (capped) result = OUT_CAPPED;
 
+	if constexpr (SWEEP) {
+		// static sweep: the same straight-line work in every lane (loa_sweep.cuh)
+		const RowCounts rc = sweep_rows(s.my, s.en, f.lut);
+		const u32 n = play ? rc.n : 0u;
+		const bool act = n != 0;
+		u32 idx = 0;
+		if (act) {
+			if ((s.ply >> 2) != s.rq) { s.rq = s.ply >> 2; rnd = gai::choice_block(key, id, s.rq); }
+			idx = gai::choice_index(pick_word(rnd, s.ply), n);
+		}
+		int from, dir;
+		sweep_select(rc, idx, act, s.my, s.en, f.lut, f.sqt, &from, &dir);
+		if (play) {
+			bool cap = false;
+			if (act) {
+				const int to = move_target(s.my.R | s.en.R, from, dir, f.ld, f.rd);
+				cap = (s.en.R >> to) & 1ull;
+				apply_move_fast(s.my, s.en, from, to, f.sqt);
+			}
+			const Side t = s.my; s.my = s.en; s.en = t;
+			s.side ^= 1u;
+			s.ply += 1;
+			s.chk_en = act; s.chk_my = cap;
+		}
+		return result;
+	}
 	// move generation: per own piece four LUT lookups; all lanes iterate for the warp-wide maximum piece count
 	// (one REDUX), the piece's square is parked in shared memory ([piece][thread] bytes, conflict-free)
 	u64 rest = play ? s.my.R : 0ull;
@@ -202,7 +230,8 @@ __global__ void k_order_leaves(const uint8_t* __restrict__ pcount, u32 n, u32* _
 	order[off + atomicAdd(hist + 32 + pc, 1u)] = i;
 }
 
-__global__ void __launch_bounds__(1024, 1)
+template <bool SWEEP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm, const u32* __restrict__ order,
                u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
                u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
@@ -245,7 +274,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 			}
 		}
 		if (__all_sync(FULL, exhausted)) break;
-		const int o = wstep(s, !exhausted, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
+		const int o = wstep<SWEEP>(s, !exhausted, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
 		if (o >= 0) {
 			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
 			my_plies += s.ply; my_playouts += 1;
@@ -278,6 +307,38 @@ k_movegen_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ states, 
 			int from, to;
 			nth_move(m, my.R, en.R, k, f.ld, f.rd, &from, &to);
 			outp[2 * k] = (uint8_t)from; outp[2 * k + 1] = (uint8_t)to;
+		}
+	}
+}
+
+// the same sweep through count + rank-select of the static-sweep formulation (every move k selected on its own)
+__global__ void __launch_bounds__(256, 1)
+k_movegen_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, uint8_t* __restrict__ counts, uint8_t* __restrict__ moves)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem(smem, g_lut);
+	const u32 stride = gridDim.x * blockDim.x;
+	for (u32 base = blockIdx.x * blockDim.x; base < n; base += stride) {          // whole warps stay together (REDUX inside)
+		const u32 i = base + threadIdx.x;
+		const bool live = i < n;
+		Side my{0, 0, 0, 0}, en{0, 0, 0, 0};
+		if (live) {
+			const u64 w = states[3 * (size_t)i], b = states[3 * (size_t)i + 1];
+			const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
+			my = make_side(side ? b : w, f.sqt); en = make_side(side ? w : b, f.sqt);
+		}
+		const RowCounts rc = sweep_rows(my, en, f.lut);
+		const u32 cnt = live ? rc.n : 0u;
+		if (live) counts[i] = (uint8_t)cnt;
+		const u32 maxn = __reduce_max_sync(0xffffffffu, cnt);
+		for (u32 k = 0; k < maxn; ++k) {
+			int from, dir;
+			sweep_select(rc, k, k < cnt, my, en, f.lut, f.sqt, &from, &dir);
+			if (k < cnt && k < GAI_LOA_MAX_MOVES_K) {
+				uint8_t* outp = moves + (size_t)i * 2 * GAI_LOA_MAX_MOVES_K;
+				outp[2 * k] = (uint8_t)from;
+				outp[2 * k + 1] = (uint8_t)move_target(my.R | en.R, from, dir, f.ld, f.rd);
+			}
 		}
 	}
 }
@@ -347,7 +408,11 @@ void loa_fast_build_lut_host(uint16_t* lut)
 cudaError_t loa_fast_prepare()
 {
 	cudaError_t e;
-	if ((e = cudaFuncSetAttribute(k_rollout_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_movegen_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_movegen_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_successor_hash_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	return cudaFuncSetAttribute(k_playout_trace_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
@@ -363,13 +428,19 @@ void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, u
 
 void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, const uint32_t* d_order, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
                              uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
-                             int threads, int sms, cudaStream_t st)
+                             int threads, int sms, int sweep, cudaStream_t st)
 {
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	const int blocks = fast_grid(total > 0xffffffffull ? 0xffffffffu : (uint32_t)total, threads, sms);
-	k_rollout_fast<<<blocks, threads, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies,
-	                                                          key, first_id, d_out, (u64*)d_stats, d_counter);
+#define GAI_RL_ARGS (const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, d_out, (u64*)d_stats, d_counter
+	if (!sweep) k_rollout_fast<false, 1024><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+	else if (threads > 768) k_rollout_fast<true, 1024><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+	else if (threads > 512) k_rollout_fast<true, 768><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+	else k_rollout_fast<true, 512><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+#undef GAI_RL_ARGS
 }
+void launch_loa_movegen_sweep(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
+{ if (n) k_movegen_sweep<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
 void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
 { if (n) k_movegen_fast<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
 void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uint32_t n, uint64_t* d_hash, uint32_t* d_bad, int sms, cudaStream_t st)

@@ -29,7 +29,7 @@ def ref_oracle():
     return r
 
 
-@pytest.fixture(scope="session", params=[1, 0], ids=["lut", "bitboard"])
+@pytest.fixture(scope="session", params=[2, 1, 0], ids=["sweep", "lut", "bitboard"])
 def gpu(request):
     """The engine, once per device formulation of the rules (both must be bit-exact against the oracle)."""
     import gameai_b200 as g
