@@ -45,6 +45,7 @@ struct gai_ctx {
 	int threads = 256, blocks_per_sm = 4;   // baseline kernel launch shape
 	int impl = 1;                           // 0 = baseline bitboard rules (loa_rules.cuh), 1 = rotated boards + line LUT (loa_fast.cuh)
 	int fast_threads = 1024;                // one CTA per SM for the LUT kernels
+	int sweep_threads = 768;                // the static-sweep kernel keeps 28 line words live: 78 registers -> 768 threads
 	void* d_lut = nullptr;
 	// scratch
 	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc, d_prep;
@@ -118,7 +119,7 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
 		LAUNCHED("k_prepare_leaves"); ctx->launches += 1;      // + k_order_leaves
 		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
-		                        ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2, ctx->stream);
+		                        ctx->impl == 2 ? ctx->sweep_threads : ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2, ctx->stream);
 	} else
 		launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
@@ -235,6 +236,7 @@ int gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm
 	if (threads_per_block) {
 		if (threads_per_block < 32 || threads_per_block > 1024 || (threads_per_block & 31)) return fail(ctx, GAI_ERR_INVALID, "threads_per_block must be a multiple of 32 in [32,1024]");
 		ctx->fast_threads = threads_per_block;
+		ctx->sweep_threads = threads_per_block;
 		ctx->threads = threads_per_block > 256 ? 256 : threads_per_block;
 	}
 	if (blocks_per_sm) {

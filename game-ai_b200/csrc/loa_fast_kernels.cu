@@ -128,7 +128,7 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 			idx = gai::choice_index(pick_word(rnd, s.ply), n);
 		}
 		int from, dir;
-		sweep_select(rc, idx, act, s.my, s.en, f.lut, f.sqt, &from, &dir);
+		sweep_select(rc, idx, &from, &dir);
 		if (play) {
 			bool cap = false;
 			if (act) {
@@ -330,11 +330,10 @@ k_movegen_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states,
 		const RowCounts rc = sweep_rows(my, en, f.lut);
 		const u32 cnt = live ? rc.n : 0u;
 		if (live) counts[i] = (uint8_t)cnt;
-		const u32 maxn = __reduce_max_sync(0xffffffffu, cnt);
-		for (u32 k = 0; k < maxn; ++k) {
+		for (u32 k = 0; k < cnt; ++k) {
 			int from, dir;
-			sweep_select(rc, k, k < cnt, my, en, f.lut, f.sqt, &from, &dir);
-			if (k < cnt && k < GAI_LOA_MAX_MOVES_K) {
+			sweep_select(rc, k, &from, &dir);
+			if (k < GAI_LOA_MAX_MOVES_K) {
 				uint8_t* outp = moves + (size_t)i * 2 * GAI_LOA_MAX_MOVES_K;
 				outp[2 * k] = (uint8_t)from;
 				outp[2 * k + 1] = (uint8_t)move_target(my.R | en.R, from, dir, f.ld, f.rd);

@@ -11,8 +11,8 @@
 //              row (D1 after a 16-bit rotation by 2k), so the per-row totals are a POSITIONAL popcount over 24 words:
 //              a carry-save adder tree on bit planes (LOP3 only), folded to 6-bit counts and spread to byte lanes with
 //              integer multiplies (FMA pipe).  A byte-lane prefix sum gives n and the row that holds move idx.
-//   3. piece : inside that row the reference order is by column, then direction: walk the (1-3) own pieces of the row
-//              with the per-piece lookup.
+//   3. piece : inside that row the reference order is by column, then direction: the row's 8 x 8 move bits are
+//              gathered from the line words with shifts and rotations, interleaved, and rank-selected.  No lookups.
 // Move ORDER is the reference's (LinesOfActionZasady.cpp:180-223): ascending square, then W E N S SW NE SE NW.
 #pragma once
 #include "loa_fast.cuh"
@@ -31,12 +31,16 @@ template <int K> struct D2Ph { static constexpr u32 a = (0xffu << (K + 1)) & 0xf
 
 template <int K> __device__ __forceinline__ u32 sweep_r(const Side& my, const Side& en, const uint16_t* lut) { return lut16(lut, static_byte<K>(my.R), static_byte<K>(en.R)); }
 template <int K> __device__ __forceinline__ u32 sweep_c(const Side& my, const Side& en, const uint16_t* lut) { return lut16(lut, static_byte<K>(my.C), static_byte<K>(en.C)); }
-template <int K, class PH> __device__ __forceinline__ u32 sweep_diag(u64 myb, u64 enb, const uint16_t* lut)
+// The phantom masks are OR-ed into whole registers (4 bytes at a time) before the byte extraction: myA = board | PHA.
+template <template <int> class PH> struct PhWords {
+	static constexpr u64 A = (u64)PH<0>::a | ((u64)PH<1>::a << 8) | ((u64)PH<2>::a << 16) | ((u64)PH<3>::a << 24) | ((u64)PH<4>::a << 32) | ((u64)PH<5>::a << 40) | ((u64)PH<6>::a << 48) | ((u64)PH<7>::a << 56);
+	static constexpr u64 B = (u64)PH<0>::b | ((u64)PH<1>::b << 8) | ((u64)PH<2>::b << 16) | ((u64)PH<3>::b << 24) | ((u64)PH<4>::b << 32) | ((u64)PH<5>::b << 40) | ((u64)PH<6>::b << 48) | ((u64)PH<7>::b << 56);
+};
+template <int K, class PH> __device__ __forceinline__ u32 sweep_diag(u64 myA, u64 enA, u64 myB, u64 enB, const uint16_t* lut)
 {
-	const u32 o = static_byte<K>(myb), e = static_byte<K>(enb);
 	u32 v = 0;
-	if (PH::len_a >= 2) v = lut16(lut, o | PH::a, e | PH::a);          // a one-cell line has no moves
-	if (PH::len_b >= 2) v |= lut16(lut, o | PH::b, e | PH::b);         // the two lines own disjoint cells
+	if (PH::len_a >= 2) v = lut16(lut, static_byte<K>(myA), static_byte<K>(enA));      // a one-cell line has no moves
+	if (PH::len_b >= 2) v |= lut16(lut, static_byte<K>(myB), static_byte<K>(enB));     // the two lines own disjoint cells
 	return v;
 }
 __device__ __forceinline__ u32 rotl16(u32 x, int s)                     // x < 65536, 0 <= s < 16
@@ -51,6 +55,8 @@ __device__ __forceinline__ FullAdd fa(u32 a, u32 b, u32 c) { FullAdd r; r.s = a 
 struct RowCounts {
 	u32 plo, phi;      // inclusive prefix sums of the per-row move totals, one byte per row (rows 0-3 / 4-7)
 	u32 n;             // total number of legal moves
+	u32 rp[4];         // R words, two per register (rows 2j | 2j+1 << 16), fields by column
+	u32 w[12];         // C (w0-3), D2 (w4-7), D1 rotated (w8-11) words, two per register, fields by ROW
 };
 
 // steps 1 + 2.  Every lane executes exactly this straight-line code.
@@ -63,21 +69,25 @@ __device__ __forceinline__ RowCounts sweep_rows(const Side& my, const Side& en, 
 	u32 thi = (u32)__popc(r4) + ((u32)__popc(r5) << 8) + ((u32)__popc(r6) << 16) + ((u32)__popc(r7) << 24);
 
 	// ---- C, D1, D2 lines: one cell per row; two 16-bit words per register
-	u32 w[12];
+	RowCounts rc;
+	u32* w = rc.w;
+	rc.rp[0] = r0 | (r1 << 16); rc.rp[1] = r2 | (r3 << 16); rc.rp[2] = r4 | (r5 << 16); rc.rp[3] = r6 | (r7 << 16);
 	w[0] = sweep_c<0>(my, en, lut) | (sweep_c<1>(my, en, lut) << 16);
 	w[1] = sweep_c<2>(my, en, lut) | (sweep_c<3>(my, en, lut) << 16);
 	w[2] = sweep_c<4>(my, en, lut) | (sweep_c<5>(my, en, lut) << 16);
 	w[3] = sweep_c<6>(my, en, lut) | (sweep_c<7>(my, en, lut) << 16);
 	// D2: cell = row already
-	w[4] = sweep_diag<0, D2Ph<0>>(my.D2, en.D2, lut) | (sweep_diag<1, D2Ph<1>>(my.D2, en.D2, lut) << 16);
-	w[5] = sweep_diag<2, D2Ph<2>>(my.D2, en.D2, lut) | (sweep_diag<3, D2Ph<3>>(my.D2, en.D2, lut) << 16);
-	w[6] = sweep_diag<4, D2Ph<4>>(my.D2, en.D2, lut) | (sweep_diag<5, D2Ph<5>>(my.D2, en.D2, lut) << 16);
-	w[7] = sweep_diag<6, D2Ph<6>>(my.D2, en.D2, lut) | (sweep_diag<7, D2Ph<7>>(my.D2, en.D2, lut) << 16);
+	const u64 m2a = my.D2 | PhWords<D2Ph>::A, e2a = en.D2 | PhWords<D2Ph>::A, m2b = my.D2 | PhWords<D2Ph>::B, e2b = en.D2 | PhWords<D2Ph>::B;
+	const u64 m1a = my.D1 | PhWords<D1Ph>::A, e1a = en.D1 | PhWords<D1Ph>::A, m1b = my.D1 | PhWords<D1Ph>::B, e1b = en.D1 | PhWords<D1Ph>::B;
+	w[4] = sweep_diag<0, D2Ph<0>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<1, D2Ph<1>>(m2a, e2a, m2b, e2b, lut) << 16);
+	w[5] = sweep_diag<2, D2Ph<2>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<3, D2Ph<3>>(m2a, e2a, m2b, e2b, lut) << 16);
+	w[6] = sweep_diag<4, D2Ph<4>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<5, D2Ph<5>>(m2a, e2a, m2b, e2b, lut) << 16);
+	w[7] = sweep_diag<6, D2Ph<6>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<7, D2Ph<7>>(m2a, e2a, m2b, e2b, lut) << 16);
 	// D1: cell = column c, row = (c + k) & 7  ->  rotate the 2-bit fields left by k cells
-	w[8]  = sweep_diag<0, D1Ph<0>>(my.D1, en.D1, lut) | (rotl16(sweep_diag<1, D1Ph<1>>(my.D1, en.D1, lut), 2) << 16);
-	w[9]  = rotl16(sweep_diag<2, D1Ph<2>>(my.D1, en.D1, lut), 4) | (rotl16(sweep_diag<3, D1Ph<3>>(my.D1, en.D1, lut), 6) << 16);
-	w[10] = rotl16(sweep_diag<4, D1Ph<4>>(my.D1, en.D1, lut), 8) | (rotl16(sweep_diag<5, D1Ph<5>>(my.D1, en.D1, lut), 10) << 16);
-	w[11] = rotl16(sweep_diag<6, D1Ph<6>>(my.D1, en.D1, lut), 12) | (rotl16(sweep_diag<7, D1Ph<7>>(my.D1, en.D1, lut), 14) << 16);
+	w[8]  = sweep_diag<0, D1Ph<0>>(m1a, e1a, m1b, e1b, lut) | (rotl16(sweep_diag<1, D1Ph<1>>(m1a, e1a, m1b, e1b, lut), 2) << 16);
+	w[9]  = rotl16(sweep_diag<2, D1Ph<2>>(m1a, e1a, m1b, e1b, lut), 4) | (rotl16(sweep_diag<3, D1Ph<3>>(m1a, e1a, m1b, e1b, lut), 6) << 16);
+	w[10] = rotl16(sweep_diag<4, D1Ph<4>>(m1a, e1a, m1b, e1b, lut), 8) | (rotl16(sweep_diag<5, D1Ph<5>>(m1a, e1a, m1b, e1b, lut), 10) << 16);
+	w[11] = rotl16(sweep_diag<6, D1Ph<6>>(m1a, e1a, m1b, e1b, lut), 12) | (rotl16(sweep_diag<7, D1Ph<7>>(m1a, e1a, m1b, e1b, lut), 14) << 16);
 
 	// positional popcount of the 12 registers: carry-save adders on bit planes
 	const FullAdd a0 = fa(w[0], w[1], w[2]), a1 = fa(w[3], w[4], w[5]), a2 = fa(w[6], w[7], w[8]), a3 = fa(w[9], w[10], w[11]);
@@ -106,42 +116,74 @@ __device__ __forceinline__ RowCounts sweep_rows(const Side& my, const Side& en, 
 	thi += GAI_SPREAD_HI(z1) + GAI_SPREAD_HI(z2.s) * 2u + GAI_SPREAD_HI(z4.s) * 4u + GAI_SPREAD_HI(z8.s) * 8u + GAI_SPREAD_HI(z16.s) * 16u + GAI_SPREAD_HI(z16.c) * 32u;
 #undef GAI_SPREAD_LO
 #undef GAI_SPREAD_HI
-	RowCounts rc;
 	rc.plo = tlo * BM;                                   // byte i = rows 0..i   (n <= 96 < 256: no byte overflows)
 	rc.phi = thi * BM + (rc.plo >> 24) * BM;
 	rc.n = rc.phi >> 24;
 	return rc;
 }
 
-// step 3: the idx-th move (reference order) -> (from, direction)
-// Warp-collective (one REDUX): every lane of the warp must call it; lanes with valid == false do no work.
-__device__ __forceinline__ void sweep_select(const RowCounts& rc, u32 idx, bool valid, const Side& my, const Side& en,
-                                             const uint16_t* __restrict__ lut, const u64* __restrict__ sqt, int* from, int* dir)
+// step 3: the idx-th move (reference order) -> (from, direction).  Straight-line code, no lookups: the moves of
+// the selected row are gathered from the line words (one 2-bit field per column and orientation), interleaved into the
+// reference order (column, then W E | N S | SW NE | SE NW) and rank-selected.
+__device__ __forceinline__ u32 spread2to4(u32 x)          // 8 two-bit fields (16 bits) -> 8 nibbles
+{
+	x = (x | (x << 8)) & 0x00ff00ffu;
+	x = (x | (x << 4)) & 0x0f0f0f0fu;
+	x = (x | (x << 2)) & 0x33333333u;
+	return x;
+}
+__device__ __forceinline__ u32 spread4to8(u32 x)          // 4 nibbles (16 bits) -> 4 bytes
+{
+	x = (x | (x << 8)) & 0x00ff00ffu;
+	x = (x | (x << 4)) & 0x0f0f0f0fu;
+	return x;
+}
+// field `sh/2` of each of the 8 words packed in p[0..3] -> 16-bit word, word j's field placed at position POS(j)
+template <int P0, int P1, int P2, int P3, int P4, int P5, int P6, int P7>
+__device__ __forceinline__ u32 gather_fields(const u32* p, u32 sh)
+{
+	const u32 t0 = (p[0] >> sh) & 0x00030003u, t1 = (p[1] >> sh) & 0x00030003u, t2 = (p[2] >> sh) & 0x00030003u, t3 = (p[3] >> sh) & 0x00030003u;
+	return ((t0 & 3u) << (2 * P0)) | ((t0 >> 16) << (2 * P1)) | ((t1 & 3u) << (2 * P2)) | ((t1 >> 16) << (2 * P3))
+	     | ((t2 & 3u) << (2 * P4)) | ((t2 >> 16) << (2 * P5)) | ((t3 & 3u) << (2 * P6)) | ((t3 >> 16) << (2 * P7));
+}
+__device__ __forceinline__ void sweep_select(const RowCounts& rc, u32 idx, int* from, int* dir)
 {
 	// row = number of rows whose inclusive prefix is <= idx   (SWAR byte compare, all values < 128)
 	const u32 y = (idx + 1u) * 0x01010101u;
 	const u32 glo = ((rc.plo | 0x80808080u) - y) & 0x80808080u, ghi = ((rc.phi | 0x80808080u) - y) & 0x80808080u;
-	const int row = 8 - __popc(glo) - __popc(ghi);
+	const u32 row = (u32)(8 - __popc(glo) - __popc(ghi)) & 7u;
 	u32 k = idx;
-	if (row > 0) k -= __byte_perm(rc.plo, rc.phi, (u32)((row - 1) & 7)) & 0xffu;
-	// own pieces of that row, ascending column
-	u32 rowbits = valid ? (byte_of(my.R, (u32)(row & 7)) & 0xffu) : 0u;
-	const int maxp = __reduce_max_sync(0xffffffffu, __popc(rowbits));
-	int f = 0, d = 0; bool found = false;
-	for (int j = 0; j < maxp; ++j) {
-		if (rowbits != 0 && !found) {
-			const int c = __ffs((int)rowbits) - 1;
-			rowbits &= rowbits - 1;
-			const int sq = row * 8 + c;
-			u32 v = piece_moves_fast(my, en, sq, lut, sqt);
-			const u32 cnt = (u32)__popc(v);
-			if (k < cnt) {
-				for (u32 t = 0; t < k; ++t) v &= v - 1;            // k <= 7
-				f = sq; d = __ffs((int)v) - 1; found = true;
-			} else k -= cnt;
-		}
-	}
-	*from = f; *dir = d;
+	if (row > 0) k -= __byte_perm(rc.plo, rc.phi, row - 1u) & 0xffu;
+	const u32 sh = 2u * row;
+	// R: the row's own word (fields by column: W, E)
+	const u32 rsel = (row & 4u) ? ((row & 2u) ? rc.rp[3] : rc.rp[2]) : ((row & 2u) ? rc.rp[1] : rc.rp[0]);
+	const u32 xr = (rsel >> (16u * (row & 1u))) & 0xffffu;
+	// C: field `row` of column word c -> position c; the field holds (S, N), the reference wants (N, S)
+	const u32 xc0 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 0, sh);
+	const u32 xc = ((xc0 & 0x5555u) << 1) | ((xc0 >> 1) & 0x5555u);
+	// D2: byte k = (row + c) & 7  ->  column c = (k - row) & 7 : gather by k, rotate right by `row` fields
+	const u32 y2 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 4, sh);
+	const u32 x2 = rotl16(y2, (int)((16u - sh) & 15u));
+	// D1 (rotated words): byte k = (row - c) & 7 -> column c = (row - k) & 7 : gather reversed ((8-k)&7), rotate left by `row`
+	const u32 y1 = gather_fields<0, 7, 6, 5, 4, 3, 2, 1>(rc.w + 8, sh);
+	const u32 x1 = rotl16(y1, (int)sh);
+	// interleave: byte c of z = xr[c] | xc[c] << 2 | x1[c] << 4 | x2[c] << 6
+	const u32 a = spread2to4(xr) | (spread2to4(xc) << 2);          // nibble c = R,C fields
+	const u32 b = spread2to4(x1) | (spread2to4(x2) << 2);          // nibble c = D1,D2 fields
+	const u32 zlo = spread4to8(a & 0xffffu) | (spread4to8(b & 0xffffu) << 4);
+	const u32 zhi = spread4to8(a >> 16) | (spread4to8(b >> 16) << 4);
+	// k-th set bit of (zhi:zlo), branch free
+	const u32 clo = (u32)__popc(zlo);
+	const bool hi = k >= clo;
+	u32 x = hi ? zhi : zlo; k -= hi ? clo : 0u;
+	int pos = hi ? 32 : 0;
+	{ u32 c = __popc(x & 0xffffu); bool g = k >= c; k -= g ? c : 0u; pos += g ? 16 : 0; x = g ? x >> 16 : x;
+	  c = __popc(x & 0xffu); g = k >= c; k -= g ? c : 0u; pos += g ? 8 : 0; x = g ? x >> 8 : x;
+	  c = __popc(x & 0xfu); g = k >= c; k -= g ? c : 0u; pos += g ? 4 : 0; x = g ? x >> 4 : x;
+	  c = __popc(x & 0x3u); g = k >= c; k -= g ? c : 0u; pos += g ? 2 : 0; x = g ? x >> 2 : x;
+	  pos += (k >= (x & 1u)) ? 1 : 0; }
+	*from = (int)(row * 8u) + (pos >> 3);
+	*dir = pos & 7;
 }
 
 } // namespace loa
