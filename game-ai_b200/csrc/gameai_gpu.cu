@@ -43,7 +43,7 @@ struct gai_ctx {
 	char err[512];
 	uint64_t launches = 0;
 	int threads = 256, blocks_per_sm = 4;   // baseline kernel launch shape
-	int impl = 1;                           // 0 = baseline bitboard rules (loa_rules.cuh), 1 = rotated boards + line LUT (loa_fast.cuh)
+	int impl = 2;                           // 0 = bitboard rules (loa_rules.cuh), 1 = rotated boards + line LUT per piece (loa_fast.cuh), 2 = static line sweep (loa_sweep.cuh)
 	int fast_threads = 1024;                // one CTA per SM for the LUT kernels
 	int sweep_threads = 768;                // the static-sweep kernel keeps 28 line words live: 78 registers -> 768 threads
 	void* d_lut = nullptr;

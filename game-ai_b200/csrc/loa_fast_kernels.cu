@@ -103,9 +103,12 @@ __device__ __forceinline__ bool wconnected(u64 b, bool want)
 
 // One ply for every lane with alive == true.  Returns the outcome code for lanes whose playout ended in this
 // step, -1 otherwise (also for lanes that were not alive).
+// SWEEP path: `phase` = loop iteration & 3.  Lanes start playouts only on iterations that are multiples of four, so
+// ply & 3 == phase in every lane and the Philox block (4 choice words) is refreshed by ALL lanes in the same iteration
+// (ncu on the per-lane refresh: the 60-instruction Philox block issued in 97 % of warp-plies at 8 active lanes).
 template <bool SWEEP>
 __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies, const FastSmem& f,
-                                     unsigned char* __restrict__ sq_scratch)
+                                     unsigned char* __restrict__ sq_scratch, u32 phase)
 {
 	const bool c_en = wconnected(s.en.R, alive && s.chk_en);
 	bool c_my = false;
@@ -122,11 +125,8 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 		const RowCounts rc = sweep_rows(s.my, s.en, f.lut);
 		const u32 n = play ? rc.n : 0u;
 		const bool act = n != 0;
-		u32 idx = 0;
-		if (act) {
-			if ((s.ply >> 2) != s.rq) { s.rq = s.ply >> 2; rnd = gai::choice_block(key, id, s.rq); }
-			idx = gai::choice_index(pick_word(rnd, s.ply), n);
-		}
+		if (phase == 0) rnd = gai::choice_block(key, id, s.ply >> 2);      // warp-uniform branch
+		const u32 idx = gai::choice_index(pick_word(rnd, phase), n);
 		int from, dir;
 		sweep_select(rc, idx, &from, &dir);
 		if (play) {
@@ -248,9 +248,9 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
 	rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
 
-	for (;;) {
+	for (u32 it = 0;; ++it) {
 		// refill: lanes whose playout ended pull the next (leaf, playout) item; one atomic per warp per refill round
-		const unsigned needmask = __ballot_sync(FULL, need && !exhausted);
+		const unsigned needmask = (!SWEEP || (it & 3u) == 0) ? __ballot_sync(FULL, need && !exhausted) : 0u;
 		if (needmask) {
 			const int leader = __ffs(needmask) - 1;
 			unsigned long long base = 0;
@@ -274,7 +274,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 			}
 		}
 		if (__all_sync(FULL, exhausted)) break;
-		const int o = wstep<SWEEP>(s, !exhausted, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
+		const int o = wstep<SWEEP>(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF, it & 3u);
 		if (o >= 0) {
 			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
 			my_plies += s.ply; my_playouts += 1;
