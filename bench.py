@@ -134,7 +134,7 @@ def cpu_playouts(states, ppl, first_id, threads, budget_s):
             "sample": "first %d leaves of the same corpus x %d playouts/leaf, same Philox key and ids, %d host threads" % (n_leaves, ppl, threads)}
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -163,7 +163,7 @@ def run_reference(args):
                              "plies_per_sec": tot_pl / tot_t, "mean_plies_per_playout": tot_pl / max(1, tot_p)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -177,10 +177,20 @@ def profile_constants():
     return None
 
 
+def _claim_stdout():
+    """Everything any library prints (NCCL writes its version banner to fd 1) goes to stderr; the ONE JSON line is
+    written to the real stdout through the returned file object."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
 def main():
     args = parse()
+    out = _claim_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import gameai_b200 as g
@@ -307,7 +317,7 @@ def main():
         if not args.no_cpu_baseline:
             cb = cpu_playouts(host_states, ppl, first_id, os.cpu_count() or 1, args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "plies_per_sec")}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     eng.dev_free(d_b); eng.dev_free(d_s); eng.dev_free(d_o)
     eng.close()
     if dist:
