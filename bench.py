@@ -317,6 +317,16 @@ def main():
         if not args.no_cpu_baseline:
             cb = cpu_playouts(host_states, ppl, first_id, os.cpu_count() or 1, args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "plies_per_sec")}
+            try:        # the reference's own MC::Player through selection_playOut (MCTSPlayer.cpp:387-470), 1 core, LOA opening
+                from oracle import mcts
+                rm = mcts.ref()
+                if rm is not None:
+                    r = rm.select(0x0081818181818100, 0x7e0000000000007e, 1, 500, seed=1234)
+                    line["cpu_baseline"]["reference_mctsplayer"] = {
+                        "simulations_per_sec": r["sims_per_sec"], "move_sim_limit": 500, "mean_path_plies": r["mean_path"], "cores": 1,
+                        "what": "reference MC::Player (oracle/_ref/libref_mcts.so), run_config_loa.xml parameters, opening position"}
+            except Exception as e:      # reported baseline only; never fatal
+                line["cpu_baseline"]["reference_mctsplayer"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line), file=out, flush=True)
     eng.dev_free(d_b); eng.dev_free(d_s); eng.dev_free(d_o)
     eng.close()

@@ -75,6 +75,7 @@ static void* load_plugin(const std::string& provider, const std::string& dir)
 enum class SingleGameResult { Win = 0, RoundLimit = 1, StateLoop = 2 };
 
 // GameController.cpp:27-115
+static std::string g_first_move;      // text of the first move made in the last game (used by --rl 1 probes)
 static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlayer*>& players, GameState* state, int round_limit, int score[], int verbose, int* rounds_out)
 {
 	const int np = (int)players.size();
@@ -86,6 +87,11 @@ static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlay
 	int round = 0;
 	for (;;) {
 		for (int i = 0; i < np; ++i) moves[i] = players[i]->selectMove(pks[i]);
+		if (round == 0) {
+			const int cp0 = rules->GetCurrentPlayer(state);
+			auto [mv0, p0] = rules->GetMoveFromList(moves[cp0], 0); (void)p0;
+			g_first_move = rules->ToString(mv0);
+		}
 		if (verbose) {
 			const int cp = rules->GetCurrentPlayer(state);
 			auto [mv, p] = rules->GetMoveFromList(moves[cp], 0); (void)p;
@@ -119,6 +125,7 @@ int main(int argc, char** argv)
 	std::string xml = "run_config_loa.xml", plugin_dir;
 	std::vector<std::string> pnames(4);
 	int num_games = -1, round_limit = -1, verbose = 0;
+	std::string start_hash;
 	unsigned seed = 12345;
 	{	// plugins live next to the executable
 		std::string self = argv[0]; size_t sl = self.find_last_of('/'); plugin_dir = sl == std::string::npos ? "." : self.substr(0, sl);
@@ -133,6 +140,7 @@ int main(int argc, char** argv)
 		else if (a == "--seed") seed = (unsigned)strtoul(next().c_str(), nullptr, 10);
 		else if (a == "--verbose" || a == "-v") verbose = 1;
 		else if (a == "--plugins") plugin_dir = next();
+		else if (a == "--start") start_hash = next();      // "white,black,cp" as hex/decimal words: play from this position
 		else if (a == "--help" || a == "-h") { std::printf("usage: GameLauncher --xml cfg.xml --p1 \"name [key=value ...]\" --p2 name [--ng N] [--rl N] [--seed S] [-v]\n"); return 0; }
 	}
 	std::ifstream f(xml);
@@ -188,7 +196,13 @@ int main(int argc, char** argv)
 	try {
 		for (int g = 0; g < num_games; ++g) {
 			int score[4] = { 0, 0, 0, 0 }, rounds = 0;
-			GameState* st = rules->CreateRandomInitialState(rng);
+			GameState* st;
+			if (start_hash.empty()) st = rules->CreateRandomInitialState(rng);
+			else {
+				uint64_t wds[3] = { 0, 0, 0 }; char* e = nullptr; const char* q = start_hash.c_str();
+				for (int k = 0; k < 3; ++k) { wds[k] = strtoull(q, &e, 0); q = (*e == ',') ? e + 1 : e; }
+				st = rules->CreateInitialStateFromHash(reinterpret_cast<const uint32_t*>(wds));       // LOA: the 24-byte state is its own hash
+			}
 			const SingleGameResult r = run_single_game(rules, players, st, round_limit, score, verbose, &rounds);
 			rounds_total += rounds;
 			if (r != SingleGameResult::Win) ++aborted;
@@ -201,7 +215,7 @@ int main(int argc, char** argv)
 	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
 	// results (the reference writes the same fields to results.xml: pN.pts / pN.win / pN.lose + player metrics, GameController.cpp:101-111,199)
-	std::printf("{\"games\": %d, \"aborted\": %d, \"rounds\": %ld, \"seconds\": %.3f, \"players\": [", num_games, aborted, rounds_total, secs);
+	std::printf("{\"games\": %d, \"aborted\": %d, \"rounds\": %ld, \"seconds\": %.3f, \"first_move\": \"%s\", \"players\": [", num_games, aborted, rounds_total, secs, g_first_move.c_str());
 	for (int i = 0; i < np; ++i) {
 		std::printf("%s{\"name\": \"%s\", \"pts\": %.1f, \"win\": %d, \"lose\": %d, \"stats\": {", i ? ", " : "", players[i]->getName().c_str(), pts[i], wins[i], loses[i]);
 		bool first = true;

@@ -200,6 +200,7 @@ struct GpuMctsPlayer : IGamePlayer
 	double total_batches = 0;
 	int world = 1, rank = 0; bool comm_ready = false;
 	int move_nbr = 0;
+	std::string last_root;                   // "visits:value_white:value_black,..." of the last move decision (merged over trees/ranks)
 
 	GpuMctsPlayer(const Settings& s, const std::vector<int>& devs) : cfg(s), devices(devs), tie_rng(s.seed) { runs_per_move.Bucket(1000); }
 	~GpuMctsPlayer() override { for (auto& t : trees) { if (rules) t.clear(); if (t.ctx) gai_destroy(t.ctx); } }
@@ -299,6 +300,11 @@ struct GpuMctsPlayer : IGamePlayer
 			else if (diff > 0) { best.clear(); best.push_back(m); bestv = v; }
 		}
 		const int pick = best.empty() ? 0 : best[best.size() == 1 ? 0 : std::uniform_int_distribution<size_t>(0, best.size() - 1)(tie_rng)];
+		{
+			std::ostringstream rs;
+			for (int m = 0; m < nm; ++m) rs << (m ? "," : "") << visits[m] << ":" << values[2 * m] << ":" << values[2 * m + 1];
+			last_root = rs.str();
+		}
 		const double secs = std::chrono::duration<double>(Clock::now() - t0).count();
 		runs_per_move.insert((long)playouts);
 		branching.insert(nm);
@@ -318,6 +324,7 @@ struct GpuMctsPlayer : IGamePlayer
 		nm["plies_per_playout"] = plies_per_playout;
 		nm["gpu_busy_fraction"] = gpu_busy;
 		nm["gpu_batches"] = total_batches;
+		nm["last_root_stats"] = last_root;
 		return nm;
 	}
 };
