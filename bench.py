@@ -188,9 +188,9 @@ def _claim_stdout():
 
 def main():
     args = parse()
-    out = _claim_stdout()
+    real_stdout = _claim_stdout()
     if args.impl == "reference":
-        return run_reference(args, out)
+        return run_reference(args, real_stdout)
 
     import torch
     import gameai_b200 as g
@@ -327,7 +327,7 @@ def main():
                         "what": "reference MC::Player (oracle/_ref/libref_mcts.so), run_config_loa.xml parameters, opening position"}
             except Exception as e:      # reported baseline only; never fatal
                 line["cpu_baseline"]["reference_mctsplayer"] = {"unavailable": str(e)[:200]}
-        print(json.dumps(line), file=out, flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     eng.dev_free(d_b); eng.dev_free(d_s); eng.dev_free(d_o)
     eng.close()
     if dist:
