@@ -78,6 +78,7 @@ def lib():
         L.gai_pan_terminal.argtypes = [_vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]
         L.gai_pan_rollout.argtypes = [_vp, _vp, _u32, _i32, _u32, _u32, _i32, _u64, _u64, _vp, _vp]
         L.gai_pan_playout_trace.argtypes = [_vp, _vp, _u32, _i32, _u32, _i32, _u64, _u64, _vp, _vp, _vp, _vp]
+        L.gai_pan_determinize.argtypes = [_vp, _i32, _i32, _u32, _u64, _u64, _vp]
         L.gai_dev_alloc.argtypes = [_vp, _u64, ctypes.POINTER(_vp)]
         L.gai_dev_free.argtypes = [_vp, _vp]
         L.gai_memcpy_h2d.argtypes = [_vp, _vp, _vp, _u64]
@@ -97,6 +98,16 @@ def philox4x32_10(ctr, key):
     c = (ctypes.c_uint32 * 4)(*ctr); k = (ctypes.c_uint32 * 2)(*key); o = (ctypes.c_uint32 * 4)()
     lib().gai_philox4x32_10(c, k, o)
     return tuple(o)
+
+
+def pan_determinize(known_state, num_players, player, n_samples, key=0x10A5EED, first_id=0):
+    """Sample complete-information deals consistent with a player's view (host only, no GPU). -> (n_samples, 5) uint64"""
+    k = np.ascontiguousarray(known_state, dtype=np.uint64).reshape(5)
+    out = np.zeros((n_samples, 5), np.uint64)
+    r = lib().gai_pan_determinize(k.ctypes.data, num_players, player, n_samples, key, first_id, out.ctypes.data)
+    if r:
+        raise GaiError(r, "gai_pan_determinize: own hand / stack not certain, or the public hand sizes do not add up to the unseen cards")
+    return out
 
 
 def pack_states(states):

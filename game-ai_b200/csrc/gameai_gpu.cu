@@ -605,6 +605,52 @@ int gai_pan_playout_trace(gai_ctx* ctx, const gai_pan_state* states, uint32_t n,
 	return pan_bad(ctx, bad);
 }
 
+int gai_pan_determinize(const gai_pan_state* known, int np, int player, uint32_t n_samples,
+                        uint64_t key, uint64_t first_id, gai_pan_state* out)
+{
+	if (!known || (!out && n_samples) || np < 2 || np > 4 || player < 0 || player >= np) return GAI_ERR_INVALID;
+	const uint64_t M48 = 0xFFFFFFFFFFFFull;
+	const uint64_t stack = known->w[0] & M48;
+	const uint64_t own = (known->w[1 + player] >> 4) & M48;
+	// own hand and stack must be certain (00 / 11)
+	auto crisp = [](uint64_t c) { return (((c >> 1) ^ c) & 0x555555555555ull) == 0; };
+	if (!crisp(stack) || !crisp(own)) return GAI_ERR_INVALID;
+	int unseen[24], nu = 0, need = 0, cnt[4] = { 0, 0, 0, 0 };
+	for (int c = 0; c < 24; ++c) if (!((stack >> (2 * c)) & 3) && !((own >> (2 * c)) & 3)) unseen[nu++] = c;
+	for (int p = 0; p < np; ++p) { cnt[p] = (int)(known->w[1 + p] & 15); if (p != player) need += cnt[p]; }
+	if (need != nu) return GAI_ERR_INVALID;              // (a count field wrapped past 15, or an inconsistent state)
+	// rule constraint: on an empty stack the player to move holds the 9 of hearts (GraWPanaZasadyV2.cpp:127-130,415-418)
+	const int cp = (int)((known->w[0] >> 48) & 7);
+	const bool pin9h = stack == 0 && cp != player && cp < np && nu > 0 && unseen[0] == 0 && cnt[cp] > 0;
+	for (uint32_t i = 0; i < n_samples; ++i) {
+		int deck[24];
+		for (int k = 0; k < nu; ++k) deck[k] = unseen[k];
+		uint32_t draw = 0; gai::Philox4 blk{};
+		const int lo = pin9h ? 1 : 0;                      // deck[0] = 9h stays out of the shuffle and is dealt to cp
+		for (int k = nu - 1; k > lo; --k) {                // Fisher-Yates, one choice word per swap
+			if ((draw & 3u) == 0) blk = gai::choice_block(key, first_id + i, draw >> 2);
+			const uint32_t j = (uint32_t)lo + gai::choice_index(blk.v[draw & 3u], (uint32_t)(k + 1 - lo));
+			++draw;
+			const int t = deck[k]; deck[k] = deck[j]; deck[j] = t;
+		}
+		gai_pan_state s; memset(&s, 0, sizeof s);
+		s.w[0] = known->w[0];
+		int at = pin9h ? 1 : 0;
+		for (int p = 0; p < np; ++p) {
+			uint64_t cards = 0;
+			if (p == player) cards = own;
+			else {
+				int take = cnt[p];
+				if (pin9h && p == cp) { cards |= 3ull; --take; }
+				for (int k = 0; k < take; ++k) cards |= 3ull << (2 * deck[at++]);
+			}
+			s.w[1 + p] = (uint64_t)cnt[p] | (cards << 4);
+		}
+		out[i] = s;
+	}
+	return GAI_OK;
+}
+
 // ---- device memory helpers -------------------------------------------------------------------------
 int gai_dev_alloc(gai_ctx* ctx, uint64_t bytes, void** d_ptr)
 {

@@ -156,6 +156,15 @@ int gai_pan_playout_trace(gai_ctx* ctx, const gai_pan_state* states, uint32_t n,
                           uint64_t philox_key, uint64_t first_playout_id, uint8_t* code, uint32_t* plies, int32_t* value,
                           gai_pan_state* final_states);
 
+/* Determinization (HOST, no GPU; new behaviour -- the reference has no sampler, it searches the fuzzy state directly,
+ * GraWPanaZasadyV2.cpp:214-243 + MCTSPlayer.h:55-69).  `known` is what CreatePlayerKnownState gives `player`: own
+ * cards certain (11), every unseen card marked 11/10/01 in every other hand, hand sizes public.  Writes n_samples
+ * complete-information states: the unseen cards dealt uniformly at random (Fisher-Yates on the Philox stream
+ * (key, id = first_sample_id + i)) to the other players according to their public counts.  Sample i is a pure
+ * function of (known, key, first_sample_id + i).  Returns GAI_ERR_INVALID if the counts cannot be met. */
+int gai_pan_determinize(const gai_pan_state* known, int num_players, int player, uint32_t n_samples,
+                        uint64_t philox_key, uint64_t first_sample_id, gai_pan_state* out);
+
 /* ---- synthetic corpus -------------------------------------------------------- */
 /* "reachable" positions: state i = the position after k_i random plies from the opening
  * (LinesOfActionZasady.cpp:358-365), k_i = philox(key^GEN, i, 0) % max_k, moves drawn from stream

@@ -84,3 +84,21 @@ def test_rollout_full_size_properties(gpu, po):
     for i in range(0, n, 1021):
         orr, _ = po.playout_batch(npl, S[i:i + 1], ppl, 50, 1, 11, i * ppl)
         assert (orr[0] == r[i]).all()
+
+
+def test_determinized_views_roll_out(gpu, po):
+    """config 5 end to end: a player's fuzzy view -> sampled deals (host) -> batched rollouts per deal (GPU) == oracle"""
+    import gameai_b200 as g
+    npl = 3
+    full = po.gen_reachable(npl, 40, 808, 30)
+    deals = []
+    for i, s in enumerate(full):
+        cnt = [int(s[1 + p]) & 15 for p in range(npl)]
+        if sum(cnt) + bin(int(s[0]) & ((1 << 48) - 1)).count("1") // 2 != 24:
+            continue
+        view = po.player_known_state(npl, s, i % npl)
+        deals.append(g.pan_determinize(view, npl, i % npl, 32, key=5, first_id=100 * i))
+    D = np.concatenate(deals)
+    r, st = gpu.pan_rollout(npl, D, 8, 50, 1, 77, 0)
+    orr, oplies = po.playout_batch(npl, D, 8, 50, 1, 77, 0)
+    assert (r == orr).all() and st["plies"] == oplies
