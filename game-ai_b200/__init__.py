@@ -70,6 +70,7 @@ def lib():
         L.gai_loa_successor_hash.argtypes = [_vp, _vp, _u32, _vp]
         L.gai_loa_rollout.argtypes = [_vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp, _vp]
         L.gai_loa_rollout_async.argtypes = [_vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp]
+        L.gai_last_rollout_stats.argtypes = [_vp, _vp]
         L.gai_loa_rollout_device.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp, _vp]
         L.gai_loa_playout_trace.argtypes = [_vp, _vp, _u32, _u32, _u64, _u64, _vp, _vp, _vp]
         L.gai_loa_gen_reachable.argtypes = [_vp, _u32, _u64, _u32, _vp, _vp, _vp]
@@ -216,6 +217,15 @@ class GpuRollout:
         st = RolloutStats()
         self._ck(self.L.gai_loa_rollout(self.h, states.ctypes.data, states.shape[0], playouts_per_leaf, max_plies, key, first_id,
                                         out.ctypes.data, ctypes.byref(st)))
+        return _stats(st)
+
+    def rollout_async(self, states, out, playouts_per_leaf, max_plies, key, first_id):
+        """Enqueue and return; `out` (n,4) uint32 is valid after sync().  One batch in flight per context."""
+        self._ck(self.L.gai_loa_rollout_async(self.h, states.ctypes.data, states.shape[0], playouts_per_leaf, max_plies, key, first_id, out.ctypes.data))
+
+    def last_rollout_stats(self):
+        st = RolloutStats()
+        self._ck(self.L.gai_last_rollout_stats(self.h, ctypes.byref(st)))
         return _stats(st)
 
     def rollout_device(self, d_boards, d_stm, n_leaves, d_out, playouts_per_leaf=1, max_plies=50000, key=0x10A5EED, first_id=0):

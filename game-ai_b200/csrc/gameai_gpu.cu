@@ -386,6 +386,16 @@ int gai_loa_rollout_async(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_
 	return GAI_OK;
 }
 
+int gai_last_rollout_stats(gai_ctx* ctx, gai_rollout_stats* stats)
+{
+	if (!ctx || !stats) return GAI_ERR_INVALID;
+	if (ctx->pending_out) return fail(ctx, GAI_ERR_INVALID, "gai_last_rollout_stats: a batch is still in flight (call gai_sync first)");
+	memset(stats, 0, sizeof *stats);
+	if (!ctx->d_misc.p) return GAI_OK;
+	CU(cudaSetDevice(ctx->device));
+	return fill_stats(ctx, stats, true);
+}
+
 int gai_loa_rollout(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
                     uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id,
                     gai_loa_result* out, gai_rollout_stats* stats)

@@ -160,31 +160,55 @@ struct Tree {
 		}
 	}
 
-	// run simulations from `root` until the limit; fills the statistics
+	// Run simulations from `root` until the limit.  Two batches are pipelined: while batch A plays out on the GPU
+	// (gai_loa_rollout_async), the host selects batch B -- A's leaves already carry their virtual loss, so B explores
+	// elsewhere -- then A's results are backed up and B is launched.
+	struct Batch {
+		std::vector<Pending> pend; std::vector<gai_loa_state> leaves; std::vector<gai_loa_result> res; int nl = 0;
+		explicit Batch(int b) : pend((size_t)b), leaves((size_t)b), res((size_t)b) {}
+	};
+	long fill_batch(int root, Batch& b)
+	{
+		b.nl = 0;
+		for (int k = 0; k < cfg.batch; ++k)
+			if (select_leaf(root, b.pend[b.nl])) { memcpy(&b.leaves[b.nl], rules->GetStateHash(nodes[b.pend[b.nl].leaf].state), 24); ++b.nl; }
+		return (long)cfg.batch * cfg.ppl;
+	}
+	bool launch(Batch& b)
+	{
+		if (b.nl == 0) return true;
+		const int rc = gai_loa_rollout_async(ctx, b.leaves.data(), (uint32_t)b.nl, (uint32_t)cfg.ppl, (uint32_t)cfg.max_plies, key, next_playout_id, b.res.data());
+		if (rc != GAI_OK) { error = gai_last_error(ctx); return false; }
+		next_playout_id += (uint64_t)b.nl * cfg.ppl;
+		return true;
+	}
+	bool finish(Batch& b)
+	{
+		if (b.nl == 0) return true;
+		if (gai_sync(ctx) != GAI_OK) { error = gai_last_error(ctx); return false; }
+		gai_rollout_stats st;
+		if (gai_last_rollout_stats(ctx, &st) == GAI_OK) { playouts += st.playouts; plies += st.plies; gpu_ms += st.total_ms; }
+		++batches;
+		for (int i = 0; i < b.nl; ++i) {
+			const float half = 0.5f * (b.res[i].draws + b.res[i].capped);
+			backprop(b.pend[i].path, b.res[i].white_wins + half, b.res[i].black_wins + half);
+		}
+		b.nl = 0;
+		return true;
+	}
 	void search(int root, Clock::time_point deadline, long sim_limit)
 	{
-		std::vector<Pending> pend((size_t)cfg.batch);
-		std::vector<gai_loa_state> leaves((size_t)cfg.batch);
-		std::vector<gai_loa_result> res((size_t)cfg.batch);
-		long sims = 0;
-		do {
-			int nl = 0;
-			for (int b = 0; b < cfg.batch; ++b) {
-				if (select_leaf(root, pend[nl])) { memcpy(&leaves[nl], rules->GetStateHash(nodes[pend[nl].leaf].state), 24); ++nl; }
-				sims += cfg.ppl;
-			}
-			if (nl > 0) {
-				gai_rollout_stats st;
-				const int rc = gai_loa_rollout(ctx, leaves.data(), (uint32_t)nl, (uint32_t)cfg.ppl, (uint32_t)cfg.max_plies, key, next_playout_id, res.data(), &st);
-				if (rc != GAI_OK) { error = gai_last_error(ctx); return; }
-				next_playout_id += (uint64_t)nl * cfg.ppl;
-				playouts += st.playouts; plies += st.plies; gpu_ms += st.total_ms; ++batches;
-				for (int i = 0; i < nl; ++i) {
-					const float half = 0.5f * (res[i].draws + res[i].capped);
-					backprop(pend[i].path, res[i].white_wins + half, res[i].black_wins + half);
-				}
-			}
-		} while (sim_limit > 0 ? sims < sim_limit : Clock::now() < deadline);
+		Batch A(cfg.batch), B(cfg.batch);
+		Batch* fly = &A; Batch* next = &B;
+		long sims = fill_batch(root, *fly);
+		if (!launch(*fly)) return;
+		while (sim_limit > 0 ? sims < sim_limit : Clock::now() < deadline) {
+			sims += fill_batch(root, *next);          // overlaps the GPU run of *fly
+			if (!finish(*fly)) return;
+			if (!launch(*next)) return;
+			std::swap(fly, next);
+		}
+		finish(*fly);
 	}
 };
 

@@ -109,6 +109,9 @@ int gai_loa_rollout(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves
 int gai_loa_rollout_async(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
                           uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id, gai_loa_result* out);
 
+/* Statistics of the last rollout that completed on ctx (valid after gai_sync following gai_loa_rollout_async). */
+int gai_last_rollout_stats(gai_ctx* ctx, gai_rollout_stats* stats);
+
 /* DEVICE-resident variant (inputs already in HBM).  d_boards: n_leaves x {white,black} (16 B each,
  * 16-byte aligned); d_stm: ceil(n/32) words, bit (i&31) of word i>>5 = side to move of leaf i;
  * d_out: n_leaves x gai_loa_result (zeroed by the call); runs on the ctx stream, synchronises, fills stats. */
