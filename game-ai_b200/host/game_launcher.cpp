@@ -89,8 +89,7 @@ static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlay
 		for (int i = 0; i < np; ++i) moves[i] = players[i]->selectMove(pks[i]);
 		if (round == 0) {
 			const int cp0 = rules->GetCurrentPlayer(state);
-			auto [mv0, p0] = rules->GetMoveFromList(moves[cp0], 0); (void)p0;
-			g_first_move = rules->ToString(mv0);
+			if (rules->GetNumMoves(moves[cp0]) > 0) { auto [mv0, p0] = rules->GetMoveFromList(moves[cp0], 0); (void)p0; g_first_move = rules->ToString(mv0); }
 		}
 		if (verbose) {
 			const int cp = rules->GetCurrentPlayer(state);
@@ -110,7 +109,7 @@ static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlay
 	rules->Score(state, score);
 	if (verbose) std::printf("final state:\n%s\n", rules->ToString(state).c_str());
 	for (int i = 0; i < np; ++i) {
-		const GameResult gr = result == SingleGameResult::Win ? (score[i] == 100 ? GameResult::Win : score[i] == 0 ? GameResult::Loose : GameResult::Draw)
+		const GameResult gr = result == SingleGameResult::Win ? (score[i] == 0 ? GameResult::Loose : (np == 2 && score[i] == 50) ? GameResult::Draw : GameResult::Win)
 		                    : result == SingleGameResult::RoundLimit ? GameResult::AbortedByRoundLimit : GameResult::AbortedByStateLoop;
 		players[i]->endGame(score[i], gr);
 		rules->ReleaseGameState(pks[i]);
@@ -206,7 +205,7 @@ int main(int argc, char** argv)
 			const SingleGameResult r = run_single_game(rules, players, st, round_limit, score, verbose, &rounds);
 			rounds_total += rounds;
 			if (r != SingleGameResult::Win) ++aborted;
-			for (int i = 0; i < np; ++i) { pts[i] += score[i]; if (r == SingleGameResult::Win) { if (score[i] == 100) ++wins[i]; else if (score[i] == 0) ++loses[i]; } }
+			for (int i = 0; i < np; ++i) { pts[i] += score[i]; if (r == SingleGameResult::Win) { if (score[i] == 0) ++loses[i]; else if (!(np == 2 && score[i] == 50)) ++wins[i]; } }
 			std::printf("game %d: %s after %d rounds, score", g + 1, r == SingleGameResult::Win ? "finished" : r == SingleGameResult::RoundLimit ? "round limit" : "state loop", rounds);
 			for (int i = 0; i < np; ++i) std::printf(" %s=%d", players[i]->getName().c_str(), score[i]);
 			std::printf("\n"); std::fflush(stdout);

@@ -24,12 +24,35 @@ struct RandomPlayer : IGamePlayer
 		MoveList* ml = rules->GetPlayerLegalMoves(pks, me);
 		if (rules->GetCurrentPlayer(pks) != me) return ml;
 		const int n = rules->GetNumMoves(ml);
+		if (n == 0) return ml;
 		MoveList* sel = rules->SelectMoveFromList(ml, n > 1 ? std::uniform_int_distribution<int>(0, n - 1)(rng) : 0);
 		rules->ReleaseMoveList(ml);
 		return sel;
 	}
 	NamedMetrics_t getGameStats() override { return {}; }
 	std::string getName() override { return name; }
+	void resetStats() override {}
+	void release() override { delete this; }
+};
+
+// always the first legal move: in Pan that is the lowest playable card (reference: SimpleStrategyPlayer.cpp:10-37)
+struct LowCardPlayer : IGamePlayer
+{
+	int me; IGameRules* rules = nullptr;
+	explicit LowCardPlayer(int p) : me(p) {}
+	void startNewGame(GameState*) override {}
+	void endGame(int, GameResult) override {}
+	void setGameRules(IGameRules* gr) override { rules = gr; }
+	MoveList* selectMove(GameState* pks) override
+	{
+		MoveList* ml = rules->GetPlayerLegalMoves(pks, me);
+		if (rules->GetNumMoves(ml) == 0 || rules->GetCurrentPlayer(pks) != me) return ml;
+		MoveList* sel = rules->SelectMoveFromList(ml, 0);
+		rules->ReleaseMoveList(ml);
+		return sel;
+	}
+	NamedMetrics_t getGameStats() override { return {}; }
+	std::string getName() override { return "lowcard"; }
 	void resetStats() override {}
 	void release() override { delete this; }
 };
@@ -109,6 +132,7 @@ extern "C" IGamePlayer* createPlayer(int player_number, const PlayerConfig_t* pc
 	const unsigned seed = pc->get_optional<unsigned>("random_seed").get_value_or((unsigned)std::chrono::steady_clock::now().time_since_epoch().count());
 	const std::string name = pc->get_optional<std::string>("fullname").get_value_or(pc->get_optional<std::string>("name").get_value_or(type));
 	if (type == "random") return new RandomPlayer(player_number, seed, name);
+	if (type == "lowcard") return new LowCardPlayer(player_number);
 	if (type == "minmax") return new MinMaxPlayer(player_number, pc->get_optional<int>("search_depth").get_value_or(3),
 	                                              pc->get_optional<std::string>("eval_function").get_value_or(""), seed, name);
 	throw "invalid player type";                           // SimpleStrategyPlayer.cpp:93

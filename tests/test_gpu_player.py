@@ -38,3 +38,16 @@ def test_root_parallel_two_trees_one_process():
     # two independent trees (two contexts; on a 1-GPU box both on device 0) merged at the root
     res = run("--p1", "mcts move_time_limit=0.1 devices=0,0", "--p2", "random", "--ng", "2", "--seed", "5")
     assert res["players"][0]["win"] >= 1, res
+
+
+def test_determinized_gpu_pan_player_beats_lowcard():
+    """Config 5 end to end (the reference's published experiment, results/mcts_player.log:2): the determinized GPU
+    player in the MCTS seat against two `lowcard` players.  Tolerance: it must lose clearly fewer games than a
+    lowcard player does on average."""
+    r = subprocess.run([LAUNCHER, "--xml", os.path.join(ROOT, "run_config_pan.xml"), "--p1", "gpupan", "--p2", "lowcard", "--p3", "lowcard",
+                        "--ng", "40", "--seed", "9"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    gp, lc1, lc2 = res["players"]
+    assert float(gp["stats"]["playouts"]) > 1e5
+    assert gp["lose"] < 0.5 * (lc1["lose"] + lc2["lose"]), res

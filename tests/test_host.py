@@ -63,3 +63,40 @@ def test_gpu_player_refuses_to_play_without_a_gpu():
         pytest.skip("GPU present")
     r = run_launcher("--p1", "mcts", "--p2", "random", "--ng", "1")
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+# ---- Pan host rules plugin (createGameRules for GraWPanaZasadyV2) -----------------------------------------------
+def test_pan_host_rules_plugin_vs_oracle():
+    from oracle import pan
+    H = ctypes.CDLL(os.path.join(HOST, "libGraWPanaZasadyV2.so"))
+    vp = ctypes.c_void_p
+    H.pan_host_movegen.argtypes = [ctypes.c_int, vp, vp]; H.pan_host_apply.argtypes = [ctypes.c_int, vp, ctypes.c_uint64, vp]
+    H.pan_host_known_state.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp]; H.pan_host_score_eval.argtypes = [ctypes.c_int, vp, vp, vp, vp]
+    p = pan.port()
+    for npl in (2, 3, 4):
+        S = p.gen_reachable(npl, 500, 5, 100)
+        t, sc, e0, e1 = p.terminal_batch(npl, S)
+        for i in range(len(S)):
+            for st in (S[i], p.player_known_state(npl, S[i], i % npl)):              # complete state and a fuzzy view
+                mv = (ctypes.c_uint64 * 16)(); n = H.pan_host_movegen(npl, st.ctypes.data, mv)
+                oc, om = p.movegen_batch(npl, st[None])
+                assert n == oc[0] and list(mv[:n]) == [int(x) for x in om[0, :n]]
+                if n:
+                    out = np.zeros(5, np.uint64); H.pan_host_apply(npl, st.ctypes.data, mv[i % n], out.ctypes.data)
+                    assert (out == p.apply_batch(npl, st[None], np.array([mv[i % n]], dtype=np.uint64))[0]).all()
+            k = np.zeros(5, np.uint64); H.pan_host_known_state(npl, S[i].ctypes.data, i % npl, k.ctypes.data)
+            assert (k == p.player_known_state(npl, S[i], i % npl)).all()
+            s4 = (ctypes.c_int * 4)(); a4 = (ctypes.c_int * 4)(); b4 = (ctypes.c_int * 4)()
+            assert H.pan_host_score_eval(npl, S[i].ctypes.data, s4, a4, b4) == t[i]
+            assert list(s4[:npl]) == list(sc[i, :npl]) and list(a4[:npl]) == list(e0[i, :npl]) and list(b4[:npl]) == list(e1[i, :npl])
+
+
+def test_pan_launcher_three_players():
+    r = subprocess.run([LAUNCHER, "--xml", os.path.join(ROOT, "run_config_pan.xml"), "--p1", "random", "--p2", "lowcard", "--p3", "lowcard",
+                        "--ng", "20", "--seed", "4"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["games"] == 20 and len(res["players"]) == 3
+    finished = 20 - res["aborted"]
+    assert sum(p["lose"] for p in res["players"]) == finished                    # exactly one loser per finished game
+    assert sum(p["pts"] for p in res["players"]) == finished * 100 + res["aborted"] * 99       # 50+50 / 3 x 33 on an aborted game
