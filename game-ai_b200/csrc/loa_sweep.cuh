@@ -21,9 +21,20 @@ namespace loa {
 
 template <int I> __device__ __forceinline__ u32 static_byte(u64 x)
 {
-	return __byte_perm(I < 4 ? (u32)x : (u32)(x >> 32), 0u, 0x4440u | (u32)(I & 3));
+	const u32 r = I < 4 ? (u32)x : (u32)(x >> 32);
+	return __byte_perm(r, 0u, 0x4440u | (u32)(I & 3));
 }
-__device__ __forceinline__ u32 lut16(const uint16_t* __restrict__ lut, u32 o, u32 e) { return lut[o + e * (u32)LUT_STRIDE]; }
+// The ALU pipe (LOP3/SHF/PRMT/IADD3/LEA, half rate) is the binding unit of this kernel while the FMA pipe idles at
+// 15 %.  ptxas strength-reduces "x * 2 + base" to LEA (ALU pipe) whenever it can see the 2; c_two hides it in the
+// constant bank, so the byte address is two IMADs (FMA pipe):  addr = o * c_two + (e * 516 + lut_base).
+__constant__ u32 c_two = 2;
+__device__ __forceinline__ u32 lut16(const uint16_t* __restrict__ lut, u32 o, u32 e)
+{
+	const u32 a = o * c_two + (e * (2u * (u32)LUT_STRIDE) + (u32)__cvta_generic_to_shared(lut));
+	u32 v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
 
 // phantom masks of the two diagonals sharing byte K (compile time)
 template <int K> struct D1Ph { static constexpr u32 a = (0xffu << (8 - K)) & 0xffu, b = (1u << (8 - K)) - 1u; static constexpr int len_a = 8 - K, len_b = K; };
@@ -84,8 +95,8 @@ __device__ __forceinline__ RowCounts sweep_rows(const Side& my, const Side& en, 
 	w[6] = sweep_diag<4, D2Ph<4>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<5, D2Ph<5>>(m2a, e2a, m2b, e2b, lut) << 16);
 	w[7] = sweep_diag<6, D2Ph<6>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<7, D2Ph<7>>(m2a, e2a, m2b, e2b, lut) << 16);
 	// D1: cell = column c, row = (c + k) & 7  ->  rotate the 2-bit fields left by k cells
-	w[8]  = sweep_diag<0, D1Ph<0>>(m1a, e1a, m1b, e1b, lut) | (rotl16(sweep_diag<1, D1Ph<1>>(m1a, e1a, m1b, e1b, lut), 2) << 16);
-	w[9]  = rotl16(sweep_diag<2, D1Ph<2>>(m1a, e1a, m1b, e1b, lut), 4) | (rotl16(sweep_diag<3, D1Ph<3>>(m1a, e1a, m1b, e1b, lut), 6) << 16);
+	w[8] = sweep_diag<0, D1Ph<0>>(m1a, e1a, m1b, e1b, lut) | (rotl16(sweep_diag<1, D1Ph<1>>(m1a, e1a, m1b, e1b, lut), 2) << 16);
+	w[9] = rotl16(sweep_diag<2, D1Ph<2>>(m1a, e1a, m1b, e1b, lut), 4) | (rotl16(sweep_diag<3, D1Ph<3>>(m1a, e1a, m1b, e1b, lut), 6) << 16);
 	w[10] = rotl16(sweep_diag<4, D1Ph<4>>(m1a, e1a, m1b, e1b, lut), 8) | (rotl16(sweep_diag<5, D1Ph<5>>(m1a, e1a, m1b, e1b, lut), 10) << 16);
 	w[11] = rotl16(sweep_diag<6, D1Ph<6>>(m1a, e1a, m1b, e1b, lut), 12) | (rotl16(sweep_diag<7, D1Ph<7>>(m1a, e1a, m1b, e1b, lut), 14) << 16);
 
