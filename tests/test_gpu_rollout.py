@@ -115,3 +115,17 @@ def test_full_size_properties_1m_leaves(gpu, oracle):
             assert (oc[0] == out[i]).all(), i
     finally:
         gpu.dev_free(d_b); gpu.dev_free(d_s); gpu.dev_free(d_o)
+
+
+def test_async_rollout_matches_sync(gpu, oracle):
+    """gai_loa_rollout_async + gai_sync + gai_last_rollout_stats (the pipelined path of the host player)"""
+    import gameai_b200 as g
+    S = oracle.gen_reachable(2000, 61)
+    sync_counts, sync_st = gpu.rollout(S, 3, 50000, 17, 5)
+    out = np.zeros((len(S), 4), np.uint32)
+    gpu.rollout_async(S, out, 3, 50000, 17, 5)
+    with pytest.raises(g.GaiError):                      # one batch in flight per context
+        gpu.rollout_async(S, out, 3, 50000, 17, 5)
+    gpu.sync()
+    st = gpu.last_rollout_stats()
+    assert (out == sync_counts).all() and st["plies"] == sync_st["plies"] and st["playouts"] == sync_st["playouts"]
