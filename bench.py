@@ -273,9 +273,9 @@ def main():
         if dist:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = t.item()
         assert (pin_out == out).all(), "host-buffer path and device-resident path disagree"
-        e2e = {"value": world * n * ppl * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 16 + ((n + 31) // 32) * 4,
+        e2e = {"value": world * n * ppl * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 24,
                "d2h_bytes_per_step": n * 16, "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps,
-               "api": "gai_loa_rollout (HOST gai_loa_state[] in, HOST gai_loa_result[] out; repack + H2D + kernel + D2H inside)"}
+               "api": "gai_loa_rollout (HOST gai_loa_state[] in, HOST gai_loa_result[] out; H2D of the 24-byte states + device split + kernel + D2H inside)"}
 
     if rank == 0:
         mean_plies = all_plies / max(1, all_playouts)

@@ -359,14 +359,21 @@ static int rollout_host_enqueue(gai_ctx* ctx, const gai_loa_state* leaves, uint3
 	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: playouts_per_leaf must be >= 1");
 	if (ctx->pending_out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: a batch is already in flight on this context (call gai_sync)");
 	CU(cudaSetDevice(ctx->device));
+	const size_t sb = (size_t)n_leaves * sizeof(gai_loa_state);
 	const size_t bb = (size_t)n_leaves * 16, wb = (size_t)((n_leaves + 31u) / 32u) * 4, rb = (size_t)n_leaves * sizeof(gai_loa_result);
-	EN(ctx->h_in, bb, true); EN(ctx->h_in2, wb, true); EN(ctx->h_out, rb, true);
-	EN(ctx->d_boards, bb, false); EN(ctx->d_stm, wb, false); EN(ctx->d_out, rb, false);
-	// repack the reference's 24-byte GameState records into 16-byte boards + side bits, straight into pinned staging
-	gai_loa_pack_states(leaves, n_leaves, ctx->h_in.p, (uint32_t*)ctx->h_in2.p);
+	EN(ctx->h_out, rb, true);
+	EN(ctx->d_in, sb, false); EN(ctx->d_boards, bb, false); EN(ctx->d_stm, wb, false); EN(ctx->d_out, rb, false);
+	// The reference's 24-byte GameState records go to the device as they are and are split into 16-byte boards + side
+	// bits THERE (k_split_states): no host-side repack pass.  Pinned caller memory is DMA-ed directly; pageable memory
+	// is first copied into pinned staging so that the call may return before the transfer ran (async variant).
+	cudaPointerAttributes pa; const void* src = leaves;
+	const bool pinned = cudaPointerGetAttributes(&pa, leaves) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!pinned) { EN(ctx->h_in, sb, true); memcpy(ctx->h_in.p, leaves, sb); src = ctx->h_in.p; }
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-	CU(cudaMemcpyAsync(ctx->d_boards.p, ctx->h_in.p, bb, cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaMemcpyAsync(ctx->d_stm.p, ctx->h_in2.p, wb, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_in.p, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+	launch_loa_split_states(ctx->d_in.p, n_leaves, ctx->d_boards.p, (uint32_t*)ctx->d_stm.p, ctx->stream);
+	LAUNCHED("k_split_states");
 	int r = enqueue_rollout(ctx, ctx->d_boards.p, (const uint32_t*)ctx->d_stm.p, n_leaves, ppl, max_plies, key, first_id, ctx->d_out.p);
 	if (r) return r;
 	CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
