@@ -101,6 +101,35 @@ struct Tree {
 		for (auto& n : nodes) { rules->ReleaseMoveList(n.moves); rules->ReleaseGameState(n.state); }
 		nodes.clear(); edges.clear(); table.clear();
 	}
+	// Tree reuse with garbage collection (reference: findRootNode + freeSubTree, MCTSPlayer.cpp:219-251,330-354):
+	// keep what is reachable from the new root, free the rest, compact the arenas.  Returns the new root index.
+	int collect(int root)
+	{
+		std::vector<int> remap(nodes.size(), -1), order;
+		order.reserve(nodes.size() / 4 + 16);
+		remap[root] = 0; order.push_back(root);
+		for (size_t h = 0; h < order.size(); ++h) {                       // breadth first over the DAG
+			const Node& n = nodes[order[h]];
+			for (int i = 0; i < n.n_edges; ++i) {
+				const int c = edges[n.first_edge + i].child;
+				if (c >= 0 && remap[c] < 0) { remap[c] = (int)order.size(); order.push_back(c); }
+			}
+		}
+		std::vector<Node> nn; nn.reserve(order.size());
+		std::vector<Edge> ne; ne.reserve(edges.size() / 4 + 64);
+		for (int old : order) {
+			Node n = nodes[old];
+			const int fe = (int)ne.size();
+			for (int i = 0; i < n.n_edges; ++i) { Edge e = edges[n.first_edge + i]; if (e.child >= 0) e.child = remap[e.child]; ne.push_back(e); }
+			n.first_edge = fe; n.visit_id = 0;
+			nn.push_back(n);
+		}
+		for (size_t i = 0; i < nodes.size(); ++i) if (remap[i] < 0) { rules->ReleaseMoveList(nodes[i].moves); rules->ReleaseGameState(nodes[i].state); }
+		nodes.swap(nn); edges.swap(ne);
+		table.clear(); visit_id = 0;
+		for (size_t i = 0; i < nodes.size(); ++i) table.emplace(key_of(nodes[i].state), (int)i);
+		return 0;
+	}
 
 	// UCB choice among the moves that do not lead back into the current path (MCTSPlayer.cpp:564-599)
 	int choose_edge(const Node& n)
@@ -225,6 +254,7 @@ struct GpuMctsPlayer : IGamePlayer
 	int world = 1, rank = 0; bool comm_ready = false;
 	int move_nbr = 0;
 	std::string last_root;                   // "visits:value_white:value_black,..." of the last move decision (merged over trees/ranks)
+	double gc_runs = 0, gc_freed = 0, reused_visits = 0;
 
 	GpuMctsPlayer(const Settings& s, const std::vector<int>& devs) : cfg(s), devices(devs), tie_rng(s.seed) { runs_per_move.Bucket(1000); }
 	~GpuMctsPlayer() override { for (auto& t : trees) { if (rules) t.clear(); if (t.ctx) gai_destroy(t.ctx); } }
@@ -285,9 +315,10 @@ struct GpuMctsPlayer : IGamePlayer
 		std::vector<int> roots(trees.size());
 		for (size_t i = 0; i < trees.size(); ++i) {
 			Tree& t = trees[i];
-			if (t.nodes.size() > 1500000) t.clear();                                  // bounded memory: drop the tree, keep playing
 			roots[i] = t.make_node(rules->CopyGameState(pks));                        // reuses the subtree when the state is known
+			if (t.nodes.size() > 200000) { const size_t before = t.nodes.size(); roots[i] = t.collect(roots[i]); gc_freed += before - t.nodes.size(); ++gc_runs; }
 			t.playouts = t.plies = t.batches = 0; t.gpu_ms = 0;
+			reused_visits += t.nodes[roots[i]].visits;                               // > 0 when the position was found in the old tree
 		}
 		// rules pools are not thread safe (GameController.cpp:167-180): extra trees get their own rules instance? No --
 		// the host rules plugin here allocates per call, so one instance is shared read-mostly; searches run one thread per tree.
@@ -349,6 +380,7 @@ struct GpuMctsPlayer : IGamePlayer
 		nm["gpu_busy_fraction"] = gpu_busy;
 		nm["gpu_batches"] = total_batches;
 		nm["last_root_stats"] = last_root;
+		nm["tree_gc_runs"] = gc_runs; nm["tree_gc_freed_nodes"] = gc_freed; nm["reused_root_visits"] = reused_visits;
 		return nm;
 	}
 };

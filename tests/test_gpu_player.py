@@ -51,3 +51,12 @@ def test_determinized_gpu_pan_player_beats_lowcard():
     gp, lc1, lc2 = res["players"]
     assert float(gp["stats"]["playouts"]) > 1e5
     assert gp["lose"] < 0.5 * (lc1["lose"] + lc2["lose"]), res
+
+
+def test_tree_reuse_and_gc():
+    # a long search per move grows the tree past the GC threshold; the root of the next decision is found in the old
+    # tree (reference: findRootNode, MCTSPlayer.cpp:219-251) and unreachable nodes are freed
+    res = run("--p1", "mcts move_time_limit=0.3 gpu_batch=2048 playouts_per_leaf=8", "--p2", "random", "--ng", "1", "--seed", "12")
+    st = res["players"][0]["stats"]
+    assert float(st["reused_root_visits"]) > 0 and float(st["tree_gc_runs"]) >= 1 and float(st["tree_gc_freed_nodes"]) > 0
+    assert res["players"][0]["win"] == 1
