@@ -173,7 +173,7 @@ __global__ void k_playout_trace(const u64* __restrict__ states, u32 n, u32 max_p
 }
 
 // synthetic "reachable" corpus (see gameai_gpu.h gai_loa_gen_reachable)
-__global__ void k_gen_reachable(u32 n, u64 key, u32 max_k, ulonglong2* __restrict__ boards, u32* __restrict__ stm_bytes_unused,
+__global__ void k_gen_reachable(u32 n, u64 key, u32 max_k, ulonglong2* __restrict__ boards,
                                 u64* __restrict__ states24, uint8_t* __restrict__ side_out)
 {
 	__shared__ u64 s_ld[64], s_rd[64];
@@ -252,7 +252,7 @@ void launch_loa_playout_trace(const void* d_states, uint32_t n, uint32_t max_pli
                               uint8_t* d_outcome, uint32_t* d_plies, void* d_final, cudaStream_t st)
 { if (n) k_playout_trace<<<nblk(n, 128), 128, 0, st>>>((const u64*)d_states, n, max_plies, key, first_id, d_outcome, d_plies, (u64*)d_final); }
 void launch_loa_gen_reachable(uint32_t n, uint64_t key, uint32_t max_k, void* d_boards, void* d_states24, uint8_t* d_side, cudaStream_t st)
-{ if (n) k_gen_reachable<<<nblk(n, 128), 128, 0, st>>>(n, key, max_k, (ulonglong2*)d_boards, nullptr, (u64*)d_states24, d_side); }
+{ if (n) k_gen_reachable<<<nblk(n, 128), 128, 0, st>>>(n, key, max_k, (ulonglong2*)d_boards, (u64*)d_states24, d_side); }
 void launch_loa_pack_stm(const uint8_t* d_side, uint32_t n, uint32_t* d_stm, cudaStream_t st)
 { if (n) k_pack_stm<<<nblk(n, 256), 256, 0, st>>>(d_side, n, d_stm); }
 void launch_loa_split_states(const void* d_states24, uint32_t n, void* d_boards, uint32_t* d_stm, cudaStream_t st)
