@@ -26,7 +26,10 @@
 
 namespace loa {
 
-constexpr int LUT_STRIDE = 258;
+#ifndef GAI_LUT_STRIDE
+#define GAI_LUT_STRIDE 258
+#endif
+constexpr int LUT_STRIDE = GAI_LUT_STRIDE;        // even, >= 256; LUT_STRIDE / 2 odd spreads the enemy byte over the banks
 constexpr int LUT_ENTRIES = LUT_STRIDE * 255 + 256;          // 66046
 constexpr int LUT_BYTES = ((LUT_ENTRIES * 2 + 15) / 16) * 16; // 132096
 

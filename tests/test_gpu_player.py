@@ -19,12 +19,13 @@ def run(*args):
 
 def test_gpu_mcts_beats_random_and_shallow_alphabeta():
     # win-rate tolerance: a uniformly random mover (or a 2-ply search with the rules' constant eval, which is
-    # what the reference's MinMaxAB sees on LOA) must lose essentially every game to 0.1 s of MCTS
-    res = run("--p1", "mcts move_time_limit=0.1", "--p2", "random", "--ng", "4", "--seed", "3")
+    # what the reference's MinMaxAB sees on LOA) must lose essentially every game to 300 k playouts of MCTS per move
+    # (fixed seeds and a simulation budget instead of a time budget: the games are reproducible)
+    res = run("--p1", "mcts move_sim_limit=300000 random_seed=21 philox_seed=22", "--p2", "random random_seed=23", "--ng", "4", "--seed", "3")
     assert res["players"][0]["win"] >= 3, res
     stats = res["players"][0]["stats"]
     assert float(stats["playouts_per_sec"]) > 1e5 and float(stats["gpu_batches"]) > 0
-    res = run("--p1", "ab3 search_depth=2", "--p2", "mcts move_time_limit=0.1", "--ng", "3", "--seed", "4")
+    res = run("--p1", "ab3 search_depth=2 random_seed=31", "--p2", "mcts move_sim_limit=300000 random_seed=32 philox_seed=33", "--ng", "3", "--seed", "4")
     assert res["players"][1]["win"] >= 2, res
 
 
@@ -36,7 +37,7 @@ def test_fixed_simulation_budget_is_reproducible():
 
 def test_root_parallel_two_trees_one_process():
     # two independent trees (two contexts; on a 1-GPU box both on device 0) merged at the root
-    res = run("--p1", "mcts move_time_limit=0.1 devices=0,0", "--p2", "random", "--ng", "2", "--seed", "5")
+    res = run("--p1", "mcts move_time_limit=0.1 devices=0,0 random_seed=41 philox_seed=42", "--p2", "random random_seed=43", "--ng", "2", "--seed", "5")
     assert res["players"][0]["win"] >= 1, res
 
 
@@ -56,7 +57,7 @@ def test_determinized_gpu_pan_player_beats_lowcard():
 def test_tree_reuse_and_gc():
     # a long search per move grows the tree past the GC threshold; the root of the next decision is found in the old
     # tree (reference: findRootNode, MCTSPlayer.cpp:219-251) and unreachable nodes are freed
-    res = run("--p1", "mcts move_time_limit=0.3 gpu_batch=2048 playouts_per_leaf=8", "--p2", "random", "--ng", "1", "--seed", "12")
+    res = run("--p1", "mcts move_sim_limit=2000000 gpu_batch=2048 playouts_per_leaf=8 random_seed=51 philox_seed=52", "--p2", "random random_seed=53", "--ng", "1", "--seed", "12")
     st = res["players"][0]["stats"]
     assert float(st["reused_root_visits"]) > 0 and float(st["tree_gc_runs"]) >= 1 and float(st["tree_gc_freed_nodes"]) > 0
     assert res["players"][0]["lose"] == 0
