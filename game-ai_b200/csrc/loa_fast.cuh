@@ -8,12 +8,12 @@
 //    ONE BYTE of one register pair:
 //        R  : byte = row r          cell = column c           (the plain bitboard, LinesOfActionZasady.cpp:43)
 //        C  : byte = column c       cell = row r              (transposed)
-//        D1 : byte = (r - c) & 7    cell = column c           ("left" diagonal A1->H8, :93-113)
+//        D1 : byte = (r - c) & 7    cell = row r              ("left" diagonal A1->H8, :93-113)
 //        D2 : byte = (r + c) & 7    cell = row r              ("right" diagonal H1->A8, :114-135)
 //    In R, D1 and D2 the reference's FIRST direction of the line (W, SW, SE -- :194-223) is "towards lower cells" and
 //    the second (E, NE, NW) "towards higher cells"; in C it is the other way round (N = higher row comes first), the
-//    two bits of a C field are swapped when a piece's move mask is assembled.  C, D2 and (after a rotation) D1 all
-//    index their cells by ROW, which is what the static sweep in loa_sweep.cuh relies on.
+//    two bits of a C field are swapped when a piece's move mask is assembled.  C, D1 and D2 all index their cells by
+//    ROW, which is what the static sweep in loa_sweep.cuh relies on (its per-row totals are a vertical sum).
 //    A D1/D2 byte holds two complementary diagonals (lengths k and 8-k); the cells of the other diagonal are
 //    presented to the LUT as "phantom" cells.
 //  * one table LUT[(o8, e8)] (own / enemy occupancy of the 8 cells) -> 16 bits, 2 per cell:
@@ -59,13 +59,13 @@ __host__ __device__ inline uint16_t lut_entry(u32 o, u32 e)
 
 // rotated-board bit positions of square s = 8r + c
 __host__ __device__ constexpr int pos_c(int s)  { return 8 * (s & 7) + (s >> 3); }
-__host__ __device__ constexpr int pos_d1(int s) { return 8 * (((s >> 3) - (s & 7)) & 7) + (s & 7); }
+__host__ __device__ constexpr int pos_d1(int s) { return 8 * (((s >> 3) - (s & 7)) & 7) + (s >> 3); }
 __host__ __device__ constexpr int pos_d2(int s) { return 8 * (((s >> 3) + (s & 7)) & 7) + (s >> 3); }
 // phantom cells of the D1 / D2 byte seen from square s (cells that belong to the complementary diagonal)
 __host__ __device__ constexpr u32 phantom_d1(int s)
 {
-	const int r = s >> 3, c = s & 7, k = (r - c) & 7;
-	return (r >= c) ? ((0xffu << (8 - k)) & 0xffu) : ((1u << (8 - k)) - 1u);
+	const int r = s >> 3, c = s & 7, k = (r - c) & 7;           // r >= c: the diagonal r - c = k holds rows k..7 of the byte
+	return (r >= c) ? ((1u << k) - 1u) : ((0xffu << k) & 0xffu);   // r <  c: the diagonal r - c = k - 8 holds rows 0..k-1
 }
 __host__ __device__ constexpr u32 phantom_d2(int s)
 {
@@ -88,14 +88,14 @@ __host__ __device__ constexpr SquareTable make_square_table()
 
 struct Side { u64 R, C, D1, D2; };      // one colour, four rotations
 
-__device__ __forceinline__ u64 bit64(int p) { return 1ull << p; }
+GAI_HDI u64 bit64(int p) { return 1ull << p; }
 
 // build the rotations of one colour from its plain bitboard (once per playout)
-__device__ __forceinline__ Side make_side(u64 b, const u64* __restrict__ sqt)
+GAI_HDI Side make_side(u64 b, const u64* __restrict__ sqt)
 {
 	Side s; s.R = b; s.C = 0; s.D1 = 0; s.D2 = 0;
 	for (u64 rest = b; rest; rest &= rest - 1) {
-		const int q = __ffsll((long long)rest) - 1;
+		const int q = hd_ffsll(rest) - 1;
 		const u32 hi = (u32)(sqt[q] >> 32);
 		s.C |= bit64(hi & 63u); s.D1 |= bit64((hi >> 8) & 63u); s.D2 |= bit64((hi >> 16) & 63u);
 	}
@@ -126,7 +126,7 @@ __device__ __forceinline__ u32 piece_moves_fast(const Side& my, const Side& en, 
 	const u32 xR = (vR >> (2u * c)) & 3u;            // W, E
 	const u32 xCs = (vC >> (2u * r)) & 3u;           // bit0 = S (lower row), bit1 = N
 	const u32 xC = ((xCs >> 1) | (xCs << 1)) & 3u;   // N, S
-	const u32 x1 = (v1 >> (2u * c)) & 3u;            // SW, NE
+	const u32 x1 = (v1 >> (2u * r)) & 3u;            // SW, NE
 	const u32 x2 = (v2 >> (2u * r)) & 3u;            // SE, NW
 	return xR + xC * 4u + x1 * 16u + x2 * 64u;
 }
@@ -145,7 +145,7 @@ __device__ __forceinline__ MoveMasks all_piece_moves_fast(const Side& my, const 
 }
 
 // move the own piece from -> to in all four rotations; captures the enemy piece on `to` if any
-__device__ __forceinline__ void apply_move_fast(Side& my, Side& en, int from, int to, const u64* __restrict__ sqt)
+GAI_HDI void apply_move_fast(Side& my, Side& en, int from, int to, const u64* __restrict__ sqt)
 {
 	const u32 hf = (u32)(sqt[from] >> 32), ht = (u32)(sqt[to] >> 32);
 	const u64 tR = bit64(to), tC = bit64(ht & 63u), t1 = bit64((ht >> 8) & 63u), t2 = bit64((ht >> 16) & 63u);

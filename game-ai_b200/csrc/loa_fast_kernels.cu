@@ -122,7 +122,7 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 
 	if constexpr (SWEEP) {
 		// static sweep: the same straight-line work in every lane (loa_sweep.cuh)
-		const RowCounts rc = sweep_rows(s.my, s.en, f.lut);
+		const RowCounts rc = sweep_rows(s.my, s.en, lut_ref(f.lut));
 		const u32 n = play ? rc.n : 0u;
 		const bool act = n != 0;
 		if (phase == 0) rnd = gai::choice_block(key, id, s.ply >> 2);      // warp-uniform branch
@@ -327,7 +327,7 @@ k_movegen_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states,
 			const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
 			my = make_side(side ? b : w, f.sqt); en = make_side(side ? w : b, f.sqt);
 		}
-		const RowCounts rc = sweep_rows(my, en, f.lut);
+		const RowCounts rc = sweep_rows(my, en, lut_ref(f.lut));
 		const u32 cnt = live ? rc.n : 0u;
 		if (live) counts[i] = (uint8_t)cnt;
 		for (u32 k = 0; k < cnt; ++k) {

@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+#define GAI_HDI __host__ __device__ __forceinline__
+
 namespace loa {
 
 typedef unsigned long long u64;
@@ -19,6 +21,53 @@ constexpr u64 OPEN_BLACK = 0x7e0000000000007eull;   // LinesOfActionZasady.cpp:3
 constexpr u64 OPEN_WHITE = 0x0081818181818100ull;   // :363
 
 enum { OUT_WHITE = 0, OUT_BLACK = 1, OUT_DRAW = 2, OUT_CAPPED = 3 };
+
+// ---- intrinsics with a host twin: the formulations built on them (loa_sweep.cuh) also compile for the CPU so that
+// `pytest -m "not gpu"` (tests/helpers/host_rules.cu) checks their logic against the oracle before any GPU time is spent.
+GAI_HDI u32 hd_popc(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+	return (u32)__popc(x);
+#else
+	return (u32)__builtin_popcount(x);
+#endif
+}
+GAI_HDI u32 hd_popcll(u64 x)
+{
+#if defined(__CUDA_ARCH__)
+	return (u32)__popcll(x);
+#else
+	return (u32)__builtin_popcountll(x);
+#endif
+}
+GAI_HDI int hd_ffsll(u64 x)
+{
+#if defined(__CUDA_ARCH__)
+	return __ffsll((long long)x);
+#else
+	return __builtin_ffsll((long long)x);
+#endif
+}
+GAI_HDI u32 hd_byte_perm(u32 a, u32 b, u32 sel)           // PRMT, default mode (selector nibbles 0-7, no sign replication used here)
+{
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(a, b, sel);
+#else
+	const u64 v = (u64)a | ((u64)b << 32);
+	u32 r = 0;
+	for (int i = 0; i < 4; ++i) r |= (u32)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+	return r;
+#endif
+}
+GAI_HDI u32 hd_dp4a(u32 a, u32 b, u32 c)                  // IDP.4A.U8.U8: c + sum of the four byte products
+{
+#if defined(__CUDA_ARCH__)
+	return __dp4a(a, b, c);
+#else
+	for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+	return c;
+#endif
+}
 
 // ---- line masks (LinesOfActionZasady.cpp:82-135) --------------------------------------------------
 __host__ __device__ constexpr u64 row_mask(int p) { return 0xFFull << (p & 56); }
@@ -46,14 +95,14 @@ __host__ __device__ constexpr DiagTables make_diag_tables()
 
 // ---- connectivity (LinesOfActionZasady.cpp:52-81, 271-305) ----------------------------------------
 // 8-neighbourhood dilation of a set of squares (centre included).
-__device__ __forceinline__ u64 dilate8(u64 g)
+GAI_HDI u64 dilate8(u64 g)
 {
 	const u64 h = g | ((g << 1) & ~FILE_A) | ((g >> 1) & ~FILE_H);
 	return h | (h << 8) | (h >> 8);
 }
 // calcIfTerminal(board) (:52-58): exactly one piece, or exactly one 8-connected group.
 // Flood fill by shift-and-mask dilation from the lowest piece until the fixpoint.
-__device__ __forceinline__ bool connected(u64 b)
+GAI_HDI bool connected(u64 b)
 {
 	if (b == 0) return false;                 // 0 groups, popcount 0
 	u64 g = b & (0 - b);
@@ -67,14 +116,14 @@ __device__ __forceinline__ bool connected(u64 b)
 }
 // Cheap necessary condition used before the flood fill: a colour with >= 2 pieces cannot be connected
 // if some piece has no neighbour of its own colour.
-__device__ __forceinline__ bool has_isolated_piece(u64 b)
+GAI_HDI bool has_isolated_piece(u64 b)
 {
 	const u64 h = ((b << 1) & ~FILE_A) | ((b >> 1) & ~FILE_H);
 	const u64 v = h | b;
 	const u64 nbr = h | (v << 8) | (v >> 8);
 	return (b & ~nbr) != 0;
 }
-__device__ __forceinline__ bool connected_fast(u64 b)
+GAI_HDI bool connected_fast(u64 b)
 {
 	if (b == 0) return false;
 	if ((b & (b - 1)) == 0) return true;
@@ -84,7 +133,7 @@ __device__ __forceinline__ bool connected_fast(u64 b)
 
 // ---- move generation (LinesOfActionZasady.cpp:136-155, 167-232) -----------------------------------
 // Direction order of the reference (:194-223): 0 W(-1) 1 E(+1) 2 N(+8) 3 S(-8) 4 SW(-9) 5 NE(+9) 6 SE(-7) 7 NW(+7)
-__device__ __forceinline__ int dir_step(int d)
+GAI_HDI int dir_step(int d)
 {
 	// signed bytes -1,+1,+8,-8,-9,+9,-7,+7 packed little-endian (no local-memory table)
 	return (int)(signed char)(0x07F909F7F80801FFull >> (8 * d));
@@ -119,11 +168,11 @@ __device__ __forceinline__ u32 piece_moves(u64 my, u64 en, int pos, const u64* _
 }
 
 // target square of the move of the piece on `pos` in direction d
-__device__ __forceinline__ int move_target(u64 all, int pos, int d, const u64* __restrict__ ld, const u64* __restrict__ rd)
+GAI_HDI int move_target(u64 all, int pos, int d, const u64* __restrict__ ld, const u64* __restrict__ rd)
 {
 	const int line = d >> 1;
 	const u64 L = line == 0 ? row_mask(pos) : line == 1 ? col_mask(pos) : line == 2 ? ld[pos] : rd[pos];
-	const int n = __popcll(all & L);
+	const int n = (int)hd_popcll(all & L);
 	return pos + n * dir_step(d);
 }
 
@@ -183,7 +232,7 @@ __device__ __forceinline__ void apply_move(u64& my, u64& en, int from, int to)
 }
 
 // Score (:420-432) folded to an outcome code.
-__device__ __forceinline__ int outcome_of(bool white_conn, bool black_conn)
+GAI_HDI int outcome_of(bool white_conn, bool black_conn)
 {
 	return (white_conn && black_conn) ? OUT_DRAW : white_conn ? OUT_WHITE : OUT_BLACK;
 }

@@ -8,7 +8,7 @@
 //              two complementary diagonals) -> a 16-bit word, 2 bits per cell (may the own piece on the cell move
 //              towards lower / higher cells).  32 words, byte indices and phantom masks are compile-time constants.
 //   2. rows  : per-row move totals.  R words belong to one row each (popcount).  C / D1 / D2 words have one cell per
-//              row (D1 after a 16-bit rotation by 2k), so the per-row totals are a POSITIONAL popcount over 24 words:
+//              row, so the per-row totals are a POSITIONAL popcount over 24 words:
 //              a carry-save adder tree on bit planes (LOP3 only), folded to 6-bit counts and spread to byte lanes with
 //              integer multiplies (FMA pipe).  A byte-lane prefix sum gives n and the row that holds move idx.
 //   3. piece : inside that row the reference order is by column, then direction: the row's 8 x 8 move bits are
@@ -19,86 +19,112 @@
 
 namespace loa {
 
-template <int I> __device__ __forceinline__ u32 static_byte(u64 x)
+// The ALU pipe (LOP3/SHF/PRMT/SEL/IADD3) is the binding unit of this kernel; IMAD and IDP.4A issue on the other
+// (FMA-heavy) pipe at the same rate (profiles/r01_ubench_pipes.json: 0.5 warp-instructions / clock / sub-partition each,
+// 0.93 when interleaved).  So the LUT byte address  2 * o + 516 * e + base  is computed without touching the ALU pipe:
+// IDP.4A with a one-byte weight extracts AND scales a byte of the board register in a single instruction,
+//     t = dp4a(enemy_half, 129 << 8k, 0);  u = dp4a(own_half, 2 << 8k, base);  addr = t * 4 + u
+// and the 4 is read from the constant bank so that ptxas cannot turn the last IMAD into a LEA (ALU pipe).
+__constant__ u32 c_four = 4, c_64k = 65536;
+#if defined(__CUDA_ARCH__)
+typedef u32 LutRef;                                   // shared-memory byte address of the line LUT
+#else
+typedef const uint16_t* LutRef;                       // host twin (tests/helpers/host_rules.cu): a plain pointer
+#endif
+GAI_HDI LutRef lut_ref(const uint16_t* p)
 {
-	const u32 r = I < 4 ? (u32)x : (u32)(x >> 32);
-	return __byte_perm(r, 0u, 0x4440u | (u32)(I & 3));
+#if defined(__CUDA_ARCH__)
+	return (u32)__cvta_generic_to_shared(p);
+#else
+	return p;
+#endif
 }
-// The ALU pipe (LOP3/SHF/PRMT/IADD3/LEA, half rate) is the binding unit of this kernel while the FMA pipe idles at
-// 15 %.  ptxas strength-reduces "x * 2 + base" to LEA (ALU pipe) whenever it can see the 2; c_two hides it in the
-// constant bank, so the byte address is two IMADs (FMA pipe):  addr = o * c_two + (e * 516 + lut_base).
-__constant__ u32 c_two = 2;
-__device__ __forceinline__ u32 lut16(const uint16_t* __restrict__ lut, u32 o, u32 e)
+static_assert(LUT_STRIDE % 2 == 0 && LUT_STRIDE / 2 <= 255, "the enemy-byte weight of the LUT address must fit one dp4a byte");
+template <int I> GAI_HDI u32 lut16(LutRef lut, u64 my, u64 en)          // LUT word of byte I of a rotation
 {
-	const u32 a = o * c_two + (e * (2u * (u32)LUT_STRIDE) + (u32)__cvta_generic_to_shared(lut));
+	const u32 m = I < 4 ? (u32)my : (u32)(my >> 32), e = I < 4 ? (u32)en : (u32)(en >> 32);
+#if defined(__CUDA_ARCH__)
+	const u32 a = hd_dp4a(e, (u32)(LUT_STRIDE / 2) << (8 * (I & 3)), 0u) * c_four + hd_dp4a(m, 2u << (8 * (I & 3)), lut);
 	u32 v;
 	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
+#else
+	return lut[((m >> (8 * (I & 3))) & 0xffu) + ((e >> (8 * (I & 3))) & 0xffu) * (u32)LUT_STRIDE];
+#endif
+}
+GAI_HDI u32 pack16(u32 lo, u32 hi)                      // lo | hi << 16 (both < 65536) as one IMAD
+{
+#if defined(__CUDA_ARCH__)
+	return hi * c_64k + lo;
+#else
+	return lo | (hi << 16);
+#endif
 }
 
-// phantom masks of the two diagonals sharing byte K (compile time)
-template <int K> struct D1Ph { static constexpr u32 a = (0xffu << (8 - K)) & 0xffu, b = (1u << (8 - K)) - 1u; static constexpr int len_a = 8 - K, len_b = K; };
+// phantom masks of the two diagonals sharing byte K (compile time).  D1 byte K: the diagonal r - c = K holds rows K..7
+// (line a), the diagonal r - c = K - 8 rows 0..K-1 (line b).  D2 byte K: r + c = K holds rows 0..K, r + c = K + 8 rows K+1..7.
+template <int K> struct D1Ph { static constexpr u32 a = (1u << K) - 1u, b = (0xffu << K) & 0xffu; static constexpr int len_a = 8 - K, len_b = K; };
 template <int K> struct D2Ph { static constexpr u32 a = (0xffu << (K + 1)) & 0xffu, b = (1u << (K + 1)) - 1u; static constexpr int len_a = K + 1, len_b = 7 - K; };
 
-template <int K> __device__ __forceinline__ u32 sweep_r(const Side& my, const Side& en, const uint16_t* lut) { return lut16(lut, static_byte<K>(my.R), static_byte<K>(en.R)); }
-template <int K> __device__ __forceinline__ u32 sweep_c(const Side& my, const Side& en, const uint16_t* lut) { return lut16(lut, static_byte<K>(my.C), static_byte<K>(en.C)); }
+template <int K> GAI_HDI u32 sweep_r(const Side& my, const Side& en, LutRef lut) { return lut16<K>(lut, my.R, en.R); }
+template <int K> GAI_HDI u32 sweep_c(const Side& my, const Side& en, LutRef lut) { return lut16<K>(lut, my.C, en.C); }
 // The phantom masks are OR-ed into whole registers (4 bytes at a time) before the byte extraction: myA = board | PHA.
 template <template <int> class PH> struct PhWords {
 	static constexpr u64 A = (u64)PH<0>::a | ((u64)PH<1>::a << 8) | ((u64)PH<2>::a << 16) | ((u64)PH<3>::a << 24) | ((u64)PH<4>::a << 32) | ((u64)PH<5>::a << 40) | ((u64)PH<6>::a << 48) | ((u64)PH<7>::a << 56);
 	static constexpr u64 B = (u64)PH<0>::b | ((u64)PH<1>::b << 8) | ((u64)PH<2>::b << 16) | ((u64)PH<3>::b << 24) | ((u64)PH<4>::b << 32) | ((u64)PH<5>::b << 40) | ((u64)PH<6>::b << 48) | ((u64)PH<7>::b << 56);
 };
-template <int K, class PH> __device__ __forceinline__ u32 sweep_diag(u64 myA, u64 enA, u64 myB, u64 enB, const uint16_t* lut)
+template <int K, class PH> GAI_HDI u32 sweep_diag(u64 myA, u64 enA, u64 myB, u64 enB, LutRef lut)
 {
 	u32 v = 0;
-	if (PH::len_a >= 2) v = lut16(lut, static_byte<K>(myA), static_byte<K>(enA));      // a one-cell line has no moves
-	if (PH::len_b >= 2) v |= lut16(lut, static_byte<K>(myB), static_byte<K>(enB));     // the two lines own disjoint cells
+	if (PH::len_a >= 2) v = lut16<K>(lut, myA, enA);       // a one-cell line has no moves
+	if (PH::len_b >= 2) v |= lut16<K>(lut, myB, enB);      // the two lines own disjoint cells
 	return v;
 }
-__device__ __forceinline__ u32 rotl16(u32 x, int s)                     // x < 65536, 0 <= s < 16
+GAI_HDI u32 rotl16(u32 x, int s)                     // x < 65536, 0 <= s < 16
 {
 	const u32 d = x * 0x10001u;
 	return (d >> ((16 - s) & 15)) & 0xffffu;
 }
 
 struct FullAdd { u32 s, c; };
-__device__ __forceinline__ FullAdd fa(u32 a, u32 b, u32 c) { FullAdd r; r.s = a ^ b ^ c; r.c = (a & b) | (c & (a ^ b)); return r; }
+GAI_HDI FullAdd fa(u32 a, u32 b, u32 c) { FullAdd r; r.s = a ^ b ^ c; r.c = (a & b) | (c & (a ^ b)); return r; }
 
 struct RowCounts {
 	u32 plo, phi;      // inclusive prefix sums of the per-row move totals, one byte per row (rows 0-3 / 4-7)
 	u32 n;             // total number of legal moves
 	u32 rp[4];         // R words, two per register (rows 2j | 2j+1 << 16), fields by column
-	u32 w[12];         // C (w0-3), D2 (w4-7), D1 rotated (w8-11) words, two per register, fields by ROW
+	u32 w[12];         // C (w0-3), D2 (w4-7), D1 (w8-11) words, two per register, fields by ROW
 };
 
 // steps 1 + 2.  Every lane executes exactly this straight-line code.
-__device__ __forceinline__ RowCounts sweep_rows(const Side& my, const Side& en, const uint16_t* __restrict__ lut)
+GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, LutRef lut)
 {
 	// ---- R lines: all cells of a word lie in one row
 	const u32 r0 = sweep_r<0>(my, en, lut), r1 = sweep_r<1>(my, en, lut), r2 = sweep_r<2>(my, en, lut), r3 = sweep_r<3>(my, en, lut);
 	const u32 r4 = sweep_r<4>(my, en, lut), r5 = sweep_r<5>(my, en, lut), r6 = sweep_r<6>(my, en, lut), r7 = sweep_r<7>(my, en, lut);
-	u32 tlo = (u32)__popc(r0) + ((u32)__popc(r1) << 8) + ((u32)__popc(r2) << 16) + ((u32)__popc(r3) << 24);
-	u32 thi = (u32)__popc(r4) + ((u32)__popc(r5) << 8) + ((u32)__popc(r6) << 16) + ((u32)__popc(r7) << 24);
+	u32 tlo = hd_popc(r0) + (hd_popc(r1) << 8) + (hd_popc(r2) << 16) + (hd_popc(r3) << 24);
+	u32 thi = hd_popc(r4) + (hd_popc(r5) << 8) + (hd_popc(r6) << 16) + (hd_popc(r7) << 24);
 
 	// ---- C, D1, D2 lines: one cell per row; two 16-bit words per register
 	RowCounts rc;
 	u32* w = rc.w;
-	rc.rp[0] = r0 | (r1 << 16); rc.rp[1] = r2 | (r3 << 16); rc.rp[2] = r4 | (r5 << 16); rc.rp[3] = r6 | (r7 << 16);
-	w[0] = sweep_c<0>(my, en, lut) | (sweep_c<1>(my, en, lut) << 16);
-	w[1] = sweep_c<2>(my, en, lut) | (sweep_c<3>(my, en, lut) << 16);
-	w[2] = sweep_c<4>(my, en, lut) | (sweep_c<5>(my, en, lut) << 16);
-	w[3] = sweep_c<6>(my, en, lut) | (sweep_c<7>(my, en, lut) << 16);
-	// D2: cell = row already
+	rc.rp[0] = pack16(r0, r1); rc.rp[1] = pack16(r2, r3); rc.rp[2] = pack16(r4, r5); rc.rp[3] = pack16(r6, r7);
+	w[0] = pack16(sweep_c<0>(my, en, lut), sweep_c<1>(my, en, lut));
+	w[1] = pack16(sweep_c<2>(my, en, lut), sweep_c<3>(my, en, lut));
+	w[2] = pack16(sweep_c<4>(my, en, lut), sweep_c<5>(my, en, lut));
+	w[3] = pack16(sweep_c<6>(my, en, lut), sweep_c<7>(my, en, lut));
+	// D2: cell = row
 	const u64 m2a = my.D2 | PhWords<D2Ph>::A, e2a = en.D2 | PhWords<D2Ph>::A, m2b = my.D2 | PhWords<D2Ph>::B, e2b = en.D2 | PhWords<D2Ph>::B;
 	const u64 m1a = my.D1 | PhWords<D1Ph>::A, e1a = en.D1 | PhWords<D1Ph>::A, m1b = my.D1 | PhWords<D1Ph>::B, e1b = en.D1 | PhWords<D1Ph>::B;
-	w[4] = sweep_diag<0, D2Ph<0>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<1, D2Ph<1>>(m2a, e2a, m2b, e2b, lut) << 16);
-	w[5] = sweep_diag<2, D2Ph<2>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<3, D2Ph<3>>(m2a, e2a, m2b, e2b, lut) << 16);
-	w[6] = sweep_diag<4, D2Ph<4>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<5, D2Ph<5>>(m2a, e2a, m2b, e2b, lut) << 16);
-	w[7] = sweep_diag<6, D2Ph<6>>(m2a, e2a, m2b, e2b, lut) | (sweep_diag<7, D2Ph<7>>(m2a, e2a, m2b, e2b, lut) << 16);
-	// D1: cell = column c, row = (c + k) & 7  ->  rotate the 2-bit fields left by k cells
-	w[8] = sweep_diag<0, D1Ph<0>>(m1a, e1a, m1b, e1b, lut) | (rotl16(sweep_diag<1, D1Ph<1>>(m1a, e1a, m1b, e1b, lut), 2) << 16);
-	w[9] = rotl16(sweep_diag<2, D1Ph<2>>(m1a, e1a, m1b, e1b, lut), 4) | (rotl16(sweep_diag<3, D1Ph<3>>(m1a, e1a, m1b, e1b, lut), 6) << 16);
-	w[10] = rotl16(sweep_diag<4, D1Ph<4>>(m1a, e1a, m1b, e1b, lut), 8) | (rotl16(sweep_diag<5, D1Ph<5>>(m1a, e1a, m1b, e1b, lut), 10) << 16);
-	w[11] = rotl16(sweep_diag<6, D1Ph<6>>(m1a, e1a, m1b, e1b, lut), 12) | (rotl16(sweep_diag<7, D1Ph<7>>(m1a, e1a, m1b, e1b, lut), 14) << 16);
+	w[4] = pack16(sweep_diag<0, D2Ph<0>>(m2a, e2a, m2b, e2b, lut), sweep_diag<1, D2Ph<1>>(m2a, e2a, m2b, e2b, lut));
+	w[5] = pack16(sweep_diag<2, D2Ph<2>>(m2a, e2a, m2b, e2b, lut), sweep_diag<3, D2Ph<3>>(m2a, e2a, m2b, e2b, lut));
+	w[6] = pack16(sweep_diag<4, D2Ph<4>>(m2a, e2a, m2b, e2b, lut), sweep_diag<5, D2Ph<5>>(m2a, e2a, m2b, e2b, lut));
+	w[7] = pack16(sweep_diag<6, D2Ph<6>>(m2a, e2a, m2b, e2b, lut), sweep_diag<7, D2Ph<7>>(m2a, e2a, m2b, e2b, lut));
+	// D1: cell = row as well (word k = (r - c) & 7)
+	w[8] = pack16(sweep_diag<0, D1Ph<0>>(m1a, e1a, m1b, e1b, lut), sweep_diag<1, D1Ph<1>>(m1a, e1a, m1b, e1b, lut));
+	w[9] = pack16(sweep_diag<2, D1Ph<2>>(m1a, e1a, m1b, e1b, lut), sweep_diag<3, D1Ph<3>>(m1a, e1a, m1b, e1b, lut));
+	w[10] = pack16(sweep_diag<4, D1Ph<4>>(m1a, e1a, m1b, e1b, lut), sweep_diag<5, D1Ph<5>>(m1a, e1a, m1b, e1b, lut));
+	w[11] = pack16(sweep_diag<6, D1Ph<6>>(m1a, e1a, m1b, e1b, lut), sweep_diag<7, D1Ph<7>>(m1a, e1a, m1b, e1b, lut));
 
 	// positional popcount of the 12 registers: carry-save adders on bit planes
 	const FullAdd a0 = fa(w[0], w[1], w[2]), a1 = fa(w[3], w[4], w[5]), a2 = fa(w[6], w[7], w[8]), a3 = fa(w[9], w[10], w[11]);
@@ -136,47 +162,58 @@ __device__ __forceinline__ RowCounts sweep_rows(const Side& my, const Side& en, 
 // step 3: the idx-th move (reference order) -> (from, direction).  Straight-line code, no lookups: the moves of
 // the selected row are gathered from the line words (one 2-bit field per column and orientation), interleaved into the
 // reference order (column, then W E | N S | SW NE | SE NW) and rank-selected.
-__device__ __forceinline__ u32 spread2to4(u32 x)          // 8 two-bit fields (16 bits) -> 8 nibbles
+GAI_HDI u32 spread2to4(u32 x)          // 8 two-bit fields (16 bits) -> 8 nibbles
 {
 	x = (x | (x << 8)) & 0x00ff00ffu;
 	x = (x | (x << 4)) & 0x0f0f0f0fu;
 	x = (x | (x << 2)) & 0x33333333u;
 	return x;
 }
-__device__ __forceinline__ u32 spread4to8(u32 x)          // 4 nibbles (16 bits) -> 4 bytes
+GAI_HDI u32 spread4to8(u32 x)          // 4 nibbles (16 bits) -> 4 bytes
 {
 	x = (x | (x << 8)) & 0x00ff00ffu;
 	x = (x | (x << 4)) & 0x0f0f0f0fu;
 	return x;
 }
-// field `sh/2` of each of the 8 words packed in p[0..3] -> 16-bit word, word j's field placed at position POS(j)
-template <int P0, int P1, int P2, int P3, int P4, int P5, int P6, int P7>
-__device__ __forceinline__ u32 gather_fields(const u32* p, u32 sh)
+// Field `row` of each of the 8 words packed two per register in p[0..3] -> one 16-bit word, word j's field at 2-bit
+// position Pj.  M = 0x00030003 << 2*row isolates the field (one LOP3 per register); after that only ONE byte of each
+// 16-bit half is non-zero, so a dp4a with the weight 4^P in both bytes of the half moves the field to position P whatever
+// the row is: the sums come out scaled by 4^(row & 3) and are shifted back once at the end.  Positions 0-3 and 4-7 are
+// collected separately (a dp4a weight is one byte).  4 LOP3 + 1 SHF on the ALU pipe, the rest IDP.4A / IMAD.
+__host__ __device__ constexpr u32 gf_w(int P, bool hi) { return (hi ? (P >= 4) : (P < 4)) ? (1u << (2 * (P & 3))) * 0x0101u : 0u; }
+template <int PA, int PB, bool HI> GAI_HDI u32 gf_acc(u32 m, u32 acc)
 {
-	const u32 t0 = (p[0] >> sh) & 0x00030003u, t1 = (p[1] >> sh) & 0x00030003u, t2 = (p[2] >> sh) & 0x00030003u, t3 = (p[3] >> sh) & 0x00030003u;
-	return ((t0 & 3u) << (2 * P0)) | ((t0 >> 16) << (2 * P1)) | ((t1 & 3u) << (2 * P2)) | ((t1 >> 16) << (2 * P3))
-	     | ((t2 & 3u) << (2 * P4)) | ((t2 >> 16) << (2 * P5)) | ((t3 & 3u) << (2 * P6)) | ((t3 >> 16) << (2 * P7));
+	constexpr u32 W = gf_w(PA, HI) | (gf_w(PB, HI) << 16);
+	return W ? hd_dp4a(m, W, acc) : acc;
 }
-__device__ __forceinline__ void sweep_select(const RowCounts& rc, u32 idx, int* from, int* dir)
+template <int P0, int P1, int P2, int P3, int P4, int P5, int P6, int P7>
+GAI_HDI u32 gather_fields(const u32* p, u32 M, u32 sh4)
+{
+	const u32 m0 = p[0] & M, m1 = p[1] & M, m2 = p[2] & M, m3 = p[3] & M;
+	const u32 lo = gf_acc<P6, P7, false>(m3, gf_acc<P4, P5, false>(m2, gf_acc<P2, P3, false>(m1, gf_acc<P0, P1, false>(m0, 0u))));
+	const u32 hi = gf_acc<P6, P7, true>(m3, gf_acc<P4, P5, true>(m2, gf_acc<P2, P3, true>(m1, gf_acc<P0, P1, true>(m0, 0u))));
+	return (hi * 256u + lo) >> sh4;
+}
+GAI_HDI void sweep_select(const RowCounts& rc, u32 idx, int* from, int* dir)
 {
 	// row = number of rows whose inclusive prefix is <= idx   (SWAR byte compare, all values < 128)
 	const u32 y = (idx + 1u) * 0x01010101u;
 	const u32 glo = ((rc.plo | 0x80808080u) - y) & 0x80808080u, ghi = ((rc.phi | 0x80808080u) - y) & 0x80808080u;
-	const u32 row = (u32)(8 - __popc(glo) - __popc(ghi)) & 7u;
+	const u32 row = (u32)(8 - hd_popc(glo) - hd_popc(ghi)) & 7u;
 	u32 k = idx;
-	if (row > 0) k -= __byte_perm(rc.plo, rc.phi, row - 1u) & 0xffu;
-	const u32 sh = 2u * row;
+	if (row > 0) k -= hd_byte_perm(rc.plo, rc.phi, row - 1u) & 0xffu;
+	const u32 sh = 2u * row, sh4 = sh & 6u, M = 0x00030003u << sh;
 	// R: the row's own word (fields by column: W, E)
 	const u32 rsel = (row & 4u) ? ((row & 2u) ? rc.rp[3] : rc.rp[2]) : ((row & 2u) ? rc.rp[1] : rc.rp[0]);
 	const u32 xr = (rsel >> (16u * (row & 1u))) & 0xffffu;
 	// C: field `row` of column word c -> position c; the field holds (S, N), the reference wants (N, S)
-	const u32 xc0 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 0, sh);
+	const u32 xc0 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 0, M, sh4);
 	const u32 xc = ((xc0 & 0x5555u) << 1) | ((xc0 >> 1) & 0x5555u);
 	// D2: byte k = (row + c) & 7  ->  column c = (k - row) & 7 : gather by k, rotate right by `row` fields
-	const u32 y2 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 4, sh);
+	const u32 y2 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 4, M, sh4);
 	const u32 x2 = rotl16(y2, (int)((16u - sh) & 15u));
-	// D1 (rotated words): byte k = (row - c) & 7 -> column c = (row - k) & 7 : gather reversed ((8-k)&7), rotate left by `row`
-	const u32 y1 = gather_fields<0, 7, 6, 5, 4, 3, 2, 1>(rc.w + 8, sh);
+	// D1: byte k = (row - c) & 7 -> column c = (row - k) & 7 : gather reversed ((8-k)&7), rotate left by `row` fields
+	const u32 y1 = gather_fields<0, 7, 6, 5, 4, 3, 2, 1>(rc.w + 8, M, sh4);
 	const u32 x1 = rotl16(y1, (int)sh);
 	// interleave: byte c of z = xr[c] | xc[c] << 2 | x1[c] << 4 | x2[c] << 6
 	const u32 a = spread2to4(xr) | (spread2to4(xc) << 2);          // nibble c = R,C fields
@@ -184,14 +221,14 @@ __device__ __forceinline__ void sweep_select(const RowCounts& rc, u32 idx, int* 
 	const u32 zlo = spread4to8(a & 0xffffu) | (spread4to8(b & 0xffffu) << 4);
 	const u32 zhi = spread4to8(a >> 16) | (spread4to8(b >> 16) << 4);
 	// k-th set bit of (zhi:zlo), branch free
-	const u32 clo = (u32)__popc(zlo);
+	const u32 clo = hd_popc(zlo);
 	const bool hi = k >= clo;
 	u32 x = hi ? zhi : zlo; k -= hi ? clo : 0u;
 	int pos = hi ? 32 : 0;
-	{ u32 c = __popc(x & 0xffffu); bool g = k >= c; k -= g ? c : 0u; pos += g ? 16 : 0; x = g ? x >> 16 : x;
-	  c = __popc(x & 0xffu); g = k >= c; k -= g ? c : 0u; pos += g ? 8 : 0; x = g ? x >> 8 : x;
-	  c = __popc(x & 0xfu); g = k >= c; k -= g ? c : 0u; pos += g ? 4 : 0; x = g ? x >> 4 : x;
-	  c = __popc(x & 0x3u); g = k >= c; k -= g ? c : 0u; pos += g ? 2 : 0; x = g ? x >> 2 : x;
+	{ u32 c = hd_popc(x & 0xffffu); bool g = k >= c; k -= g ? c : 0u; pos += g ? 16 : 0; x = g ? x >> 16 : x;
+	  c = hd_popc(x & 0xffu); g = k >= c; k -= g ? c : 0u; pos += g ? 8 : 0; x = g ? x >> 8 : x;
+	  c = hd_popc(x & 0xfu); g = k >= c; k -= g ? c : 0u; pos += g ? 4 : 0; x = g ? x >> 4 : x;
+	  c = hd_popc(x & 0x3u); g = k >= c; k -= g ? c : 0u; pos += g ? 2 : 0; x = g ? x >> 2 : x;
 	  pos += (k >= (x & 1u)) ? 1 : 0; }
 	*from = (int)(row * 8u) + (pos >> 3);
 	*dir = pos & 7;

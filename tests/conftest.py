@@ -38,3 +38,23 @@ def gpu(request):
     eng.impl = request.param
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def hostlib():
+    """TEST HELPER library: the product's __host__ __device__ rule code (Pan rules, LOA line LUT, the static sweep)
+    compiled for the CPU, so that its logic is checked against the oracle without a GPU."""
+    import ctypes
+    import glob
+    import subprocess
+    so = os.path.join(ROOT, "tests", "helpers", "libhost_rules.so")
+    srcs = [os.path.join(ROOT, "tests", "helpers", "host_rules.cu")] + glob.glob(os.path.join(ROOT, "game-ai_b200", "csrc", "*.cuh")) \
+        + [os.path.join(ROOT, "include", "gameai", "philox.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
+                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "game-ai_b200", "csrc"), "-o", so, srcs[0], "-cudart", "static"])
+    H = ctypes.CDLL(so)
+    H.host_pan_movegen.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    H.host_pan_apply.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+    H.host_pan_terminal.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    return H

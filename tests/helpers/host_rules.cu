@@ -2,6 +2,8 @@
 // CPU so that `pytest -m "not gpu"` can compare them with the oracle before any GPU time is spent.
 #include "pan_rules.cuh"
 #include "loa_fast.cuh"
+#include "loa_sweep.cuh"
+#include "gameai/philox.h"
 #include <string.h>
 
 extern "C" {
@@ -38,4 +40,66 @@ int host_loa_pos_d1(int s) { return loa::pos_d1(s); }
 int host_loa_pos_d2(int s) { return loa::pos_d2(s); }
 unsigned host_loa_phantom_d1(int s) { return loa::phantom_d1(s); }
 unsigned host_loa_phantom_d2(int s) { return loa::phantom_d2(s); }
+
+// ---- the static-sweep formulation (loa_sweep.cuh) run on the CPU: count + rank-select of every move, and whole
+// playouts through sweep_rows / sweep_select / apply_move_fast (the code the rollout kernel executes per ply)
+static const uint16_t* host_lut()
+{
+	static uint16_t* lut = nullptr;
+	if (!lut) {
+		lut = new uint16_t[loa::LUT_BYTES / 2]();
+		for (unsigned e = 0; e < 256; ++e) for (unsigned o = 0; o < 256; ++o) lut[o + e * loa::LUT_STRIDE] = loa::lut_entry(o, e);
+	}
+	return lut;
+}
+static const loa::SquareTable g_sqt = loa::make_square_table();
+static const loa::DiagTables g_diag = loa::make_diag_tables();
+void host_loa_sweep_movegen_batch(const uint64_t* states, unsigned n, uint8_t* counts, uint8_t* moves)
+{
+	const uint16_t* lut = host_lut();
+	for (unsigned i = 0; i < n; ++i) {
+		const uint64_t w = states[3 * i], b = states[3 * i + 1]; const unsigned side = (unsigned)states[3 * i + 2] & 1u;
+		const loa::Side my = loa::make_side(side ? b : w, g_sqt.w), en = loa::make_side(side ? w : b, g_sqt.w);
+		const loa::RowCounts rc = loa::sweep_rows(my, en, loa::lut_ref(lut));
+		counts[i] = (uint8_t)rc.n;
+		for (unsigned k = 0; k < rc.n && k < 96; ++k) {
+			int from, dir;
+			loa::sweep_select(rc, k, &from, &dir);
+			moves[(size_t)i * 192 + 2 * k] = (uint8_t)from;
+			moves[(size_t)i * 192 + 2 * k + 1] = (uint8_t)loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd);
+		}
+	}
+}
+void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned max_plies, uint64_t key, uint64_t first_id,
+                                  uint8_t* outcome, uint32_t* plies, uint64_t* final_states)
+{
+	const uint16_t* lut = host_lut();
+	for (unsigned i = 0; i < n; ++i) {
+		unsigned side = (unsigned)states[3 * i + 2] & 1u;
+		loa::Side my = loa::make_side(side ? states[3 * i + 1] : states[3 * i], g_sqt.w), en = loa::make_side(side ? states[3 * i] : states[3 * i + 1], g_sqt.w);
+		unsigned ply = 0; int out = -1;
+		gai::Philox4 rnd{};
+		for (;;) {
+			const bool c_en = loa::connected_fast(en.R), c_my = loa::connected_fast(my.R);
+			if (c_en | c_my) { out = loa::outcome_of(side ? c_en : c_my, side ? c_my : c_en); break; }
+			if (ply >= max_plies) { out = loa::OUT_CAPPED; break; }
+			const loa::RowCounts rc = loa::sweep_rows(my, en, loa::lut_ref(lut));
+			if (rc.n) {
+				if ((ply & 3u) == 0 || ply == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
+				const unsigned idx = gai::choice_index(rnd.v[ply & 3u], rc.n);
+				int from, dir;
+				loa::sweep_select(rc, idx, &from, &dir);
+				const int to = loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd);
+				loa::apply_move_fast(my, en, from, to, g_sqt.w);
+			} else if ((ply & 3u) == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
+			const loa::Side t = my; my = en; en = t;
+			side ^= 1u; ++ply;
+		}
+		outcome[i] = (uint8_t)out; plies[i] = ply;
+		final_states[3 * i] = side ? en.R : my.R; final_states[3 * i + 1] = side ? my.R : en.R; final_states[3 * i + 2] = side;
+		// the rotations must still describe the same position
+		const loa::Side cm = loa::make_side(my.R, g_sqt.w), ce = loa::make_side(en.R, g_sqt.w);
+		if (cm.C != my.C || cm.D1 != my.D1 || cm.D2 != my.D2 || ce.C != en.C || ce.D1 != en.D1 || ce.D2 != en.D2) outcome[i] = 0xee;
+	}
+}
 }

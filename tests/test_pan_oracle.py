@@ -89,20 +89,6 @@ def test_port_vs_live_reference(po, pref):
 
 
 # ---- the product's host-callable Pan / LUT code vs the oracle (no GPU) -----------------------------------
-@pytest.fixture(scope="module")
-def hostlib():
-    so = os.path.join(ROOT, "tests", "helpers", "libhost_rules.so")
-    src = os.path.join(ROOT, "tests", "helpers", "host_rules.cu")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
-                               "-I", os.path.join(ROOT, "game-ai_b200", "csrc"), "-o", so, src, "-cudart", "static"])
-    H = ctypes.CDLL(so)
-    H.host_pan_movegen.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-    H.host_pan_apply.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
-    H.host_pan_terminal.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    return H
-
-
 def test_product_pan_rules_on_host_vs_oracle(po, hostlib):
     for npl in (2, 3, 4):
         S = po.gen_reachable(npl, 1500, 77, 100)
