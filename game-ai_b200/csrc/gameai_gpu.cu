@@ -46,6 +46,7 @@ struct gai_ctx {
 	int impl = 2;                           // 0 = bitboard rules (loa_rules.cuh), 1 = rotated boards + line LUT per piece (loa_fast.cuh), 2 = static line sweep (loa_sweep.cuh)
 	int fast_threads = 1024;                // one CTA per SM for the LUT kernels
 	int sweep_threads = 768;                // the static-sweep kernel keeps 28 line words live: 78 registers -> 768 threads
+	int sweep_unroll = 2;                   // plies per loop trip of the static-sweep kernel (1, 2, 4); GAI_SWEEP_UNROLL overrides
 	void* d_lut = nullptr;
 	// scratch
 	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc, d_prep;
@@ -119,7 +120,7 @@ int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, u
 		LAUNCHED("k_prepare_leaves"); ctx->launches += 1;      // + k_order_leaves
 		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
-		                        ctx->impl == 2 ? ctx->sweep_threads : ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2, ctx->stream);
+		                        ctx->impl == 2 ? ctx->sweep_threads : ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2 ? ctx->sweep_unroll : 0, ctx->stream);
 	} else
 		launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
@@ -163,6 +164,8 @@ int gai_create(int device, gai_ctx** out)
 		return fail(nullptr, GAI_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
 	if (device < 0 || device >= count) return fail(nullptr, GAI_ERR_INVALID, "gai_create: device ordinal out of range");
 	gai_ctx* ctx = new gai_ctx();
+	if (const char* u = getenv("GAI_SWEEP_UNROLL")) { const int v = atoi(u); if (v == 1 || v == 2 || v == 4) ctx->sweep_unroll = v; }      // tuning knob
+	if (const char* u = getenv("GAI_SWEEP_THREADS")) { const int v = atoi(u); if (v == 512 || v == 768 || v == 1024) ctx->sweep_threads = v; }
 	ctx->err[0] = 0;
 	ctx->device = device;
 	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {

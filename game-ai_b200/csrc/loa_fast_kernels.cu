@@ -191,6 +191,43 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 	return result;
 }
 
+// One ply of the static-sweep formulation with FIXED register roles: `my` moves, `en` is the side that just moved, and
+// the caller alternates the two argument orders ply by ply instead of swapping sixteen registers (the swap was 32
+// IMAD.MOV per ply).  `phase` = ply & 3 of every lane (see above); with a four-fold unrolled loop it is a constant.
+__device__ __forceinline__ int wstep_sweep(Side& my, Side& en, FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies,
+                                           const FastSmem& f, LutRef lut, u32 phase)
+{
+	const bool c_en = wconnected(en.R, alive && s.chk_en);
+	bool c_my = false;
+	if (__any_sync(FULL, alive && s.chk_my)) c_my = wconnected(my.R, alive && s.chk_my);
+	const bool term = c_en | c_my;
+	const bool capped = alive && !term && s.ply >= max_plies;
+	const bool play = alive && !term && !capped;
+	int result = -1;
+	if (term) { const bool wc = s.side ? c_en : c_my, bc = s.side ? c_my : c_en; result = outcome_of(wc, bc); }
+	if (capped) result = OUT_CAPPED;
+
+	const RowCounts rc = sweep_rows(my, en, lut);
+	const u32 n = play ? rc.n : 0u;
+	const bool act = n != 0;
+	if (phase == 0) rnd = gai::choice_block(key, id, s.ply >> 2);      // warp-uniform branch
+	const u32 idx = gai::choice_index(pick_word(rnd, phase), n);
+	int from, dir;
+	sweep_select(rc, idx, &from, &dir);
+	if (play) {
+		bool cap = false;
+		if (act) {
+			const int to = move_target(my.R | en.R, from, dir, f.ld, f.rd);
+			cap = (en.R >> to) & 1ull;
+			apply_move_fast(my, en, from, to, f.sqt);
+		}
+		s.side ^= 1u;
+		s.ply += 1;
+		s.chk_en = act; s.chk_my = cap;
+	}
+	return result;
+}
+
 // Leaf preparation: the four rotations of both colours, once per leaf (64 B = 4 x 16-byte vectors), so that a
 // lane that pulls a new playout issues four LDG.128 instead of rebuilding the rotations piece by piece while the
 // other 31 lanes of its warp wait (ncu: 6 % of all issued instructions at 1 active lane before this kernel existed).
@@ -230,7 +267,7 @@ __global__ void k_order_leaves(const uint8_t* __restrict__ pcount, u32 n, u32* _
 	order[off + atomicAdd(hist + 32 + pc, 1u)] = i;
 }
 
-template <bool SWEEP, int MAXT>
+template <bool SWEEP, int MAXT, int UNROLL>
 __global__ void __launch_bounds__(MAXT, 1)
 k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm, const u32* __restrict__ order,
                u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
@@ -248,7 +285,8 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
 	rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
 
-	for (u32 it = 0;; ++it) {
+	const LutRef lut = lut_ref(f.lut);
+	for (u32 it = 0;; it += (SWEEP ? (u32)UNROLL : 1u)) {
 		// refill: lanes whose playout ended pull the next (leaf, playout) item; one atomic per warp per refill round
 		const unsigned needmask = (!SWEEP || (it & 3u) == 0) ? __ballot_sync(FULL, need && !exhausted) : 0u;
 		if (needmask) {
@@ -274,11 +312,31 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 			}
 		}
 		if (__all_sync(FULL, exhausted)) break;
-		const int o = wstep<SWEEP>(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF, it & 3u);
-		if (o >= 0) {
-			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
-			my_plies += s.ply; my_playouts += 1;
-			need = true;
+		if constexpr (SWEEP) {
+			// UNROLL plies per trip; the two sides trade places by argument order (UNROLL is even or 1)
+#pragma unroll
+			for (int j = 0; j < UNROLL; ++j) {
+				const u32 phase = UNROLL == 4 ? (u32)j : ((it + (u32)j) & 3u);
+				int o;
+				if (UNROLL == 1) {
+					o = wstep_sweep(s.my, s.en, s, !exhausted && !need, rnd, key, pid, max_plies, f, lut, phase);
+					const Side t = s.my; s.my = s.en; s.en = t;
+				}
+				else if (j & 1) o = wstep_sweep(s.en, s.my, s, !exhausted && !need, rnd, key, pid, max_plies, f, lut, phase);
+				else o = wstep_sweep(s.my, s.en, s, !exhausted && !need, rnd, key, pid, max_plies, f, lut, phase);
+				if (o >= 0) {
+					atomicAdd(out + 4 * (size_t)leaf + o, 1u);
+					my_plies += s.ply; my_playouts += 1;
+					need = true;
+				}
+			}
+		} else {
+			const int o = wstep<false>(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF, it & 3u);
+			if (o >= 0) {
+				atomicAdd(out + 4 * (size_t)leaf + o, 1u);
+				my_plies += s.ply; my_playouts += 1;
+				need = true;
+			}
 		}
 	}
 #pragma unroll
@@ -407,10 +465,10 @@ void loa_fast_build_lut_host(uint16_t* lut)
 cudaError_t loa_fast_prepare()
 {
 	cudaError_t e;
-	if ((e = cudaFuncSetAttribute(k_rollout_fast<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
-	if ((e = cudaFuncSetAttribute(k_rollout_fast<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
-	if ((e = cudaFuncSetAttribute(k_rollout_fast<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
-	if ((e = cudaFuncSetAttribute(k_rollout_fast<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+#define GAI_PREP(T, U) if ((e = cudaFuncSetAttribute(k_rollout_fast<true, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	GAI_PREP(1024, 1) GAI_PREP(768, 1) GAI_PREP(512, 1) GAI_PREP(1024, 2) GAI_PREP(768, 2) GAI_PREP(512, 2) GAI_PREP(1024, 4) GAI_PREP(768, 4) GAI_PREP(512, 4)
+#undef GAI_PREP
 	if ((e = cudaFuncSetAttribute(k_movegen_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_movegen_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_successor_hash_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
@@ -432,10 +490,15 @@ void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	const int blocks = fast_grid(total > 0xffffffffull ? 0xffffffffu : (uint32_t)total, threads, sms);
 #define GAI_RL_ARGS (const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, d_out, (u64*)d_stats, d_counter
-	if (!sweep) k_rollout_fast<false, 1024><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
-	else if (threads > 768) k_rollout_fast<true, 1024><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
-	else if (threads > 512) k_rollout_fast<true, 768><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
-	else k_rollout_fast<true, 512><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+	// sweep: 0 = per-piece formulation, else the unroll factor of the static-sweep kernel (1, 2 or 4 plies per loop trip)
+#define GAI_RL(T, U) k_rollout_fast<true, T, U><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS)
+#define GAI_RL_T(U) do { if (threads > 768) GAI_RL(1024, U); else if (threads > 512) GAI_RL(768, U); else GAI_RL(512, U); } while (0)
+	if (!sweep) k_rollout_fast<false, 1024, 1><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+	else if (sweep >= 4) GAI_RL_T(4);
+	else if (sweep >= 2) GAI_RL_T(2);
+	else GAI_RL_T(1);
+#undef GAI_RL_T
+#undef GAI_RL
 #undef GAI_RL_ARGS
 }
 void launch_loa_movegen_sweep(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
