@@ -20,18 +20,25 @@
 //    bit 2p = own piece on cell p may move towards lower cells, bit 2p+1 = towards higher cells, by the
 //    number of pieces on the line (:191-192), not landing on an own piece (:142), not jumping an enemy
 //    (:146-148).  A cell with BOTH o and e set is a phantom: not counted, not a mover, cannot be landed on.
-//    Index = o8 + 258*e8 (the odd stride spreads (o,e) pairs over the 32 shared-memory banks).
+//    Index = o8 + 259*e8.  The stride decides the shared-memory bank of an entry, ((o + 259 e) >> 1) & 31: an ODD stride
+//    lets bit 0 of e reach the bank bits through the carry; simulated on reachable positions (32 random lanes, the 30
+//    lookups of lines longer than 4 cells) 259 costs 3.7 wavefronts per lookup, the former 258 4.8, 256 9.7.
+//  * lines of at most 4 cells (the short diagonals: 12 of the 42 lookups) live in ONE nibble of their byte; the big table
+//    hashes them badly (their varying bits fall outside the bank bits: 7-8 wavefronts).  They use a 256-entry table
+//    indexed by the two nibbles, replicated once per lane so that lane L only ever touches bank L: no conflicts at all.
 #pragma once
 #include "loa_rules.cuh"
 
 namespace loa {
 
 #ifndef GAI_LUT_STRIDE
-#define GAI_LUT_STRIDE 258
+#define GAI_LUT_STRIDE 259
 #endif
-constexpr int LUT_STRIDE = GAI_LUT_STRIDE;        // even, >= 256; LUT_STRIDE / 2 odd spreads the enemy byte over the banks
+constexpr int LUT_STRIDE = GAI_LUT_STRIDE;        // >= 256 and odd (see above); 2 * stride = 14 * 37 keeps the enemy weight a dp4a byte
 constexpr int LUT_ENTRIES = LUT_STRIDE * 255 + 256;          // 66046
-constexpr int LUT_BYTES = ((LUT_ENTRIES * 2 + 15) / 16) * 16; // 132096
+constexpr int LUT_BYTES = ((LUT_ENTRIES * 2 + 15) / 16) * 16; // 132608
+// two 256-entry u32 tables follow the line LUT in the global image (expanded to one copy per lane in shared memory)
+constexpr int SLT_OFF = LUT_BYTES, TPC_OFF = LUT_BYTES + 1024, LUT_IMAGE_BYTES = LUT_BYTES + 2048;
 
 // One LUT entry, by definition (host + device; the table is built once per context on the host).
 __host__ __device__ inline uint16_t lut_entry(u32 o, u32 e)
@@ -55,6 +62,16 @@ __host__ __device__ inline uint16_t lut_entry(u32 o, u32 e)
 		}
 	}
 	return (uint16_t)res;
+}
+
+// short-line table: 4 cells, index = own nibble + 16 * enemy nibble (a cell set in both = phantom) -> 8 bits, 2 per cell
+__host__ __device__ inline u32 slt_entry(u32 idx) { return (u32)lut_entry((idx & 15u) | 0xf0u, (idx >> 4) | 0xf0u) & 0xffu; }
+// field-count table: a byte of four 2-bit fields -> the popcount of each field in its own byte lane
+__host__ __device__ inline u32 tpc_entry(u32 b)
+{
+	u32 r = 0;
+	for (int j = 0; j < 4; ++j) { const u32 f = (b >> (2 * j)) & 3u; r |= ((f & 1u) + (f >> 1)) << (8 * j); }
+	return r;
 }
 
 // rotated-board bit positions of square s = 8r + c

@@ -11,21 +11,33 @@ __constant__ DiagTables c_diag2 = make_diag_tables();
 __constant__ SquareTable c_sqt = make_square_table();
 
 struct FastSmem {
-	const uint16_t* lut; const u64* sqt; const u64* ld; const u64* rd;
+	const uint16_t* lut; const u64* sqt; const u64* ld; const u64* rd; const u32* slt; const u32* tpc;
 };
 
-// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][64 x u64 ld][64 x u64 rd][16 x 1024 bytes piece squares]
+// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][64 x u64 ld][64 x u64 rd][tail]
+//   tail of the static-sweep kernels : [256 x 32 lanes x u32 short-line table][256 x 32 x u32 field-count table]
+//   tail of the per-piece kernels    : [16 x 1024 bytes piece squares]
 constexpr int FAST_SQ_OFF = LUT_BYTES + 3 * 64 * 8;
 constexpr int FAST_SMEM_BYTES = FAST_SQ_OFF + 16 * 1024;
+constexpr int SWEEP_SMEM_BYTES = FAST_SQ_OFF + 2 * 256 * 32 * 4;
 
+// g_lut = the global image: line LUT, then the two 256-entry tables (expanded here to one copy per lane / bank)
+template <bool SWEEP_TABLES>
 __device__ __forceinline__ FastSmem load_fast_smem(unsigned char* smem, const uint4* __restrict__ g_lut)
 {
 	uint4* d = reinterpret_cast<uint4*>(smem);
 	for (int i = threadIdx.x; i < LUT_BYTES / 16; i += blockDim.x) d[i] = __ldg(g_lut + i);
 	u64* sq = reinterpret_cast<u64*>(smem + LUT_BYTES);
 	for (int i = threadIdx.x; i < 64; i += blockDim.x) { sq[i] = c_sqt.w[i]; sq[64 + i] = c_diag2.ld[i]; sq[128 + i] = c_diag2.rd[i]; }
-	__syncthreads();
 	FastSmem f; f.lut = reinterpret_cast<const uint16_t*>(smem); f.sqt = sq; f.ld = sq + 64; f.rd = sq + 128;
+	f.slt = f.tpc = nullptr;
+	if (SWEEP_TABLES) {
+		u32* t = reinterpret_cast<u32*>(smem + FAST_SQ_OFF);
+		const u32* g = reinterpret_cast<const u32*>(reinterpret_cast<const unsigned char*>(g_lut) + SLT_OFF);      // 512 words: slt, tpc
+		for (int i = threadIdx.x; i < 2 * 256 * 32; i += blockDim.x) t[i] = __ldg(g + (i >> 5));
+		f.slt = t; f.tpc = t + 256 * 32;
+	}
+	__syncthreads();
 	return f;
 }
 
@@ -103,12 +115,9 @@ __device__ __forceinline__ bool wconnected(u64 b, bool want)
 
 // One ply for every lane with alive == true.  Returns the outcome code for lanes whose playout ended in this
 // step, -1 otherwise (also for lanes that were not alive).
-// SWEEP path: `phase` = loop iteration & 3.  Lanes start playouts only on iterations that are multiples of four, so
-// ply & 3 == phase in every lane and the Philox block (4 choice words) is refreshed by ALL lanes in the same iteration
-// (ncu on the per-lane refresh: the 60-instruction Philox block issued in 97 % of warp-plies at 8 active lanes).
-template <bool SWEEP>
+// (per-piece formulation; the static sweep has its own step below)
 __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies, const FastSmem& f,
-                                     unsigned char* __restrict__ sq_scratch, u32 phase)
+                                     unsigned char* __restrict__ sq_scratch)
 {
 	const bool c_en = wconnected(s.en.R, alive && s.chk_en);
 	bool c_my = false;
@@ -120,29 +129,6 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 	if (term) { const bool wc = s.side ? c_en : c_my, bc = s.side ? c_my : c_en; result = outcome_of(wc, bc); }
 	if (capped) result = OUT_CAPPED;
 
-	if constexpr (SWEEP) {
-		// static sweep: the same straight-line work in every lane (loa_sweep.cuh)
-		const RowCounts rc = sweep_rows(s.my, s.en, lut_ref(f.lut));
-		const u32 n = play ? rc.n : 0u;
-		const bool act = n != 0;
-		if (phase == 0) rnd = gai::choice_block(key, id, s.ply >> 2);      // warp-uniform branch
-		const u32 idx = gai::choice_index(pick_word(rnd, phase), n);
-		int from, dir;
-		sweep_select(rc, idx, &from, &dir);
-		if (play) {
-			bool cap = false;
-			if (act) {
-				const int to = move_target(s.my.R | s.en.R, from, dir, f.ld, f.rd);
-				cap = (s.en.R >> to) & 1ull;
-				apply_move_fast(s.my, s.en, from, to, f.sqt);
-			}
-			const Side t = s.my; s.my = s.en; s.en = t;
-			s.side ^= 1u;
-			s.ply += 1;
-			s.chk_en = act; s.chk_my = cap;
-		}
-		return result;
-	}
 	// move generation: per own piece four LUT lookups; all lanes iterate for the warp-wide maximum piece count
 	// (one REDUX), the piece's square is parked in shared memory ([piece][thread] bytes, conflict-free)
 	u64 rest = play ? s.my.R : 0ull;
@@ -193,9 +179,11 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 
 // One ply of the static-sweep formulation with FIXED register roles: `my` moves, `en` is the side that just moved, and
 // the caller alternates the two argument orders ply by ply instead of swapping sixteen registers (the swap was 32
-// IMAD.MOV per ply).  `phase` = ply & 3 of every lane (see above); with a four-fold unrolled loop it is a constant.
+// IMAD.MOV per ply).  `phase` = loop iteration & 3: lanes start playouts only on iterations that are multiples of four,
+// so ply & 3 == phase in every lane and the Philox block (4 choice words) is refreshed by ALL lanes in the same iteration
+// (ncu on a per-lane refresh: the 60-instruction Philox block issued in 97 % of warp-plies at 8 active lanes).
 __device__ __forceinline__ int wstep_sweep(Side& my, Side& en, FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies,
-                                           const FastSmem& f, LutRef lut, u32 phase)
+                                           const FastSmem& f, const SweepTabs& lut, u32 phase)
 {
 	const bool c_en = wconnected(en.R, alive && s.chk_en);
 	bool c_my = false;
@@ -274,7 +262,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
                u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const FastSmem f = load_fast_smem(smem, g_lut);
+	const FastSmem f = load_fast_smem<SWEEP>(smem, g_lut);
 
 	const u64 total = (u64)n_leaves * ppl;
 	const u32 lane = threadIdx.x & 31u;
@@ -285,7 +273,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
 	rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
 
-	const LutRef lut = lut_ref(f.lut);
+	const SweepTabs lut = sweep_tabs(f.lut, f.slt, f.tpc, lane);
 	for (u32 it = 0;; it += (SWEEP ? (u32)UNROLL : 1u)) {
 		// refill: lanes whose playout ended pull the next (leaf, playout) item; one atomic per warp per refill round
 		const unsigned needmask = (!SWEEP || (it & 3u) == 0) ? __ballot_sync(FULL, need && !exhausted) : 0u;
@@ -331,7 +319,7 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 				}
 			}
 		} else {
-			const int o = wstep<false>(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF, it & 3u);
+			const int o = wstep(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
 			if (o >= 0) {
 				atomicAdd(out + 4 * (size_t)leaf + o, 1u);
 				my_plies += s.ply; my_playouts += 1;
@@ -352,7 +340,7 @@ __global__ void __launch_bounds__(1024, 1)
 k_movegen_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, uint8_t* __restrict__ counts, uint8_t* __restrict__ moves)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const FastSmem f = load_fast_smem(smem, g_lut);
+	const FastSmem f = load_fast_smem<false>(smem, g_lut);
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const u64 w = states[3 * (size_t)i], b = states[3 * (size_t)i + 1];
 		const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
@@ -374,8 +362,9 @@ __global__ void __launch_bounds__(256, 1)
 k_movegen_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, uint8_t* __restrict__ counts, uint8_t* __restrict__ moves)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const FastSmem f = load_fast_smem(smem, g_lut);
+	const FastSmem f = load_fast_smem<true>(smem, g_lut);
 	const u32 stride = gridDim.x * blockDim.x;
+	const SweepTabs tabs = sweep_tabs(f.lut, f.slt, f.tpc, threadIdx.x & 31u);
 	for (u32 base = blockIdx.x * blockDim.x; base < n; base += stride) {          // whole warps stay together (REDUX inside)
 		const u32 i = base + threadIdx.x;
 		const bool live = i < n;
@@ -385,7 +374,7 @@ k_movegen_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states,
 			const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
 			my = make_side(side ? b : w, f.sqt); en = make_side(side ? w : b, f.sqt);
 		}
-		const RowCounts rc = sweep_rows(my, en, lut_ref(f.lut));
+		const RowCounts rc = sweep_rows(my, en, tabs);
 		const u32 cnt = live ? rc.n : 0u;
 		if (live) counts[i] = (uint8_t)cnt;
 		for (u32 k = 0; k < cnt; ++k) {
@@ -405,7 +394,7 @@ __global__ void __launch_bounds__(1024, 1)
 k_successor_hash_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, u64* __restrict__ hash, u32* __restrict__ bad)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const FastSmem f = load_fast_smem(smem, g_lut);
+	const FastSmem f = load_fast_smem<false>(smem, g_lut);
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const u64 w = states[3 * (size_t)i], b = states[3 * (size_t)i + 1];
 		const u32 side = (u32)states[3 * (size_t)i + 2] & 1u;
@@ -437,7 +426,7 @@ k_playout_trace_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ st
                      uint8_t* __restrict__ outcome, u32* __restrict__ plies, u64* __restrict__ final_states)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const FastSmem f = load_fast_smem(smem, g_lut);
+	const FastSmem f = load_fast_smem<false>(smem, g_lut);
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		FastSim s; gai::Philox4 rnd;
 		fsim_init(s, states[3 * (size_t)i], states[3 * (size_t)i + 1], (u32)states[3 * (size_t)i + 2] & 1u, f);
@@ -455,21 +444,23 @@ k_playout_trace_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ st
 
 using namespace loa;
 
-int loa_fast_lut_bytes() { return LUT_BYTES; }
+int loa_fast_lut_bytes() { return LUT_IMAGE_BYTES; }
 void loa_fast_build_lut_host(uint16_t* lut)
 {
-	for (int i = 0; i < LUT_BYTES / 2; ++i) lut[i] = 0;
+	for (int i = 0; i < LUT_IMAGE_BYTES / 2; ++i) lut[i] = 0;
 	for (u32 e = 0; e < 256; ++e)
 		for (u32 o = 0; o < 256; ++o) lut[o + e * LUT_STRIDE] = lut_entry(o, e);
+	u32* small = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(lut) + SLT_OFF);
+	for (u32 i = 0; i < 256; ++i) { small[i] = slt_entry(i); small[256 + i] = tpc_entry(i); }
 }
 cudaError_t loa_fast_prepare()
 {
 	cudaError_t e;
 	if ((e = cudaFuncSetAttribute(k_rollout_fast<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
-#define GAI_PREP(T, U) if ((e = cudaFuncSetAttribute(k_rollout_fast<true, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+#define GAI_PREP(T, U) if ((e = cudaFuncSetAttribute(k_rollout_fast<true, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
 	GAI_PREP(1024, 1) GAI_PREP(768, 1) GAI_PREP(512, 1) GAI_PREP(1024, 2) GAI_PREP(768, 2) GAI_PREP(512, 2) GAI_PREP(1024, 4) GAI_PREP(768, 4) GAI_PREP(512, 4)
 #undef GAI_PREP
-	if ((e = cudaFuncSetAttribute(k_movegen_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_movegen_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_movegen_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_successor_hash_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	return cudaFuncSetAttribute(k_playout_trace_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
@@ -491,7 +482,7 @@ void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint
 	const int blocks = fast_grid(total > 0xffffffffull ? 0xffffffffu : (uint32_t)total, threads, sms);
 #define GAI_RL_ARGS (const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, d_out, (u64*)d_stats, d_counter
 	// sweep: 0 = per-piece formulation, else the unroll factor of the static-sweep kernel (1, 2 or 4 plies per loop trip)
-#define GAI_RL(T, U) k_rollout_fast<true, T, U><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS)
+#define GAI_RL(T, U) k_rollout_fast<true, T, U><<<blocks, threads, SWEEP_SMEM_BYTES, st>>>(GAI_RL_ARGS)
 #define GAI_RL_T(U) do { if (threads > 768) GAI_RL(1024, U); else if (threads > 512) GAI_RL(768, U); else GAI_RL(512, U); } while (0)
 	if (!sweep) k_rollout_fast<false, 1024, 1><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
 	else if (sweep >= 4) GAI_RL_T(4);
@@ -502,7 +493,7 @@ void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint
 #undef GAI_RL_ARGS
 }
 void launch_loa_movegen_sweep(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
-{ if (n) k_movegen_sweep<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
+{ if (n) k_movegen_sweep<<<fast_grid(n, 256, sms), 256, SWEEP_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
 void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
 { if (n) k_movegen_fast<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
 void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uint32_t n, uint64_t* d_hash, uint32_t* d_bad, int sms, cudaStream_t st)

@@ -9,8 +9,8 @@
 //              towards lower / higher cells).  32 words, byte indices and phantom masks are compile-time constants.
 //   2. rows  : per-row move totals.  R words belong to one row each (popcount).  C / D1 / D2 words have one cell per
 //              row, so the per-row totals are a POSITIONAL popcount over 24 words:
-//              a carry-save adder tree on bit planes (LOP3 only), folded to 6-bit counts and spread to byte lanes with
-//              integer multiplies (FMA pipe).  A byte-lane prefix sum gives n and the row that holds move idx.
+//              a carry-save adder tree on bit planes (LOP3 only), whose four planes are turned into byte-lane counts by a
+//              conflict-free per-lane table (FMA pipe + LSU).  A byte-lane prefix sum gives n and the row that holds move idx.
 //   3. piece : inside that row the reference order is by column, then direction: the row's 8 x 8 move bits are
 //              gathered from the line words with shifts and rotations, interleaved, and rank-selected.  No lookups.
 // Move ORDER is the reference's (LinesOfActionZasady.cpp:180-223): ascending square, then W E N S SW NE SE NW.
@@ -25,26 +25,45 @@ namespace loa {
 // IDP.4A with a one-byte weight extracts AND scales a byte of the board register in a single instruction,
 //     t = dp4a(enemy_half, 129 << 8k, 0);  u = dp4a(own_half, 2 << 8k, base);  addr = t * 4 + u
 // and the 4 is read from the constant bank so that ptxas cannot turn the last IMAD into a LEA (ALU pipe).
-__constant__ u32 c_four = 4, c_64k = 65536;
+// Multipliers read from the constant bank: ptxas cannot strength-reduce  x * c[..] + y  into LEA / SHF / LOP3 (ALU pipe),
+// it stays an IMAD.
+__constant__ u32 c_one = 1, c_two = 2, c_four = 4, c_eight = 8, c_14 = 14, c_16 = 16, c_256 = 256, c_64k = 65536;
 #if defined(__CUDA_ARCH__)
 typedef u32 LutRef;                                   // shared-memory byte address of the line LUT
+typedef u32 TabRef;                                   // shared-memory byte address of a per-lane table, this lane's column
+#define GAI_MADC(x, cname, cval, y) ((x) * cname + (y))
 #else
-typedef const uint16_t* LutRef;                       // host twin (tests/helpers/host_rules.cu): a plain pointer
+typedef const uint16_t* LutRef;                       // host twin (tests/helpers/host_rules.cu): plain pointers
+typedef const u32* TabRef;
+#define GAI_MADC(x, cname, cval, y) ((x) * (u32)(cval) + (y))
 #endif
-GAI_HDI LutRef lut_ref(const uint16_t* p)
+struct SweepTabs { LutRef lut; TabRef slt, tpc; };
+// device: the three tables in the CTA's shared memory (lut: LUT_BYTES; slt, tpc: 256 entries x 32 lanes x 4 B each)
+__device__ __forceinline__ SweepTabs sweep_tabs(const uint16_t* lut, const u32* slt, const u32* tpc, u32 lane)
 {
+	SweepTabs t{};
 #if defined(__CUDA_ARCH__)
-	return (u32)__cvta_generic_to_shared(p);
-#else
-	return p;
+	t.lut = (u32)__cvta_generic_to_shared(lut);
+	t.slt = (u32)__cvta_generic_to_shared(slt) + 4u * lane;
+	t.tpc = (u32)__cvta_generic_to_shared(tpc) + 4u * lane;
 #endif
+	return t;
 }
-static_assert(LUT_STRIDE % 2 == 0 && LUT_STRIDE / 2 <= 255, "the enemy-byte weight of the LUT address must fit one dp4a byte");
+GAI_HDI SweepTabs sweep_tabs_host(const uint16_t* lut, const u32* slt, const u32* tpc)      // host twin: three plain arrays
+{
+	SweepTabs t{};
+#if !defined(__CUDA_ARCH__)
+	t.lut = lut; t.slt = slt; t.tpc = tpc;
+#endif
+	return t;
+}
+static_assert(2 * LUT_STRIDE == 14 * 37, "the enemy-byte weight of the LUT address is 37 (one dp4a byte) times 14");
+template <int I> GAI_HDI u32 half_of(u64 x) { return I < 4 ? (u32)x : (u32)(x >> 32); }
 template <int I> GAI_HDI u32 lut16(LutRef lut, u64 my, u64 en)          // LUT word of byte I of a rotation
 {
-	const u32 m = I < 4 ? (u32)my : (u32)(my >> 32), e = I < 4 ? (u32)en : (u32)(en >> 32);
+	const u32 m = half_of<I>(my), e = half_of<I>(en);
 #if defined(__CUDA_ARCH__)
-	const u32 a = hd_dp4a(e, (u32)(LUT_STRIDE / 2) << (8 * (I & 3)), 0u) * c_four + hd_dp4a(m, 2u << (8 * (I & 3)), lut);
+	const u32 a = hd_dp4a(e, 37u << (8 * (I & 3)), 0u) * c_14 + hd_dp4a(m, 2u << (8 * (I & 3)), lut);
 	u32 v;
 	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
@@ -52,34 +71,103 @@ template <int I> GAI_HDI u32 lut16(LutRef lut, u64 my, u64 en)          // LUT w
 	return lut[((m >> (8 * (I & 3))) & 0xffu) + ((e >> (8 * (I & 3))) & 0xffu) * (u32)LUT_STRIDE];
 #endif
 }
-GAI_HDI u32 pack16(u32 lo, u32 hi)                      // lo | hi << 16 (both < 65536) as one IMAD
+// Short line in the LOW nibble of byte I (both bytes pre-masked to the nibble, phantoms OR-ed in): index o4 + 16 e4.
+// The per-lane table has a 128-byte entry pitch (32 lanes x 4 B), so the byte address is 128 o4 + 2048 e4 + lane column.
+template <int I> GAI_HDI u32 slt_low(TabRef slt, u64 my, u64 en)
 {
+	const u32 m = half_of<I>(my), e = half_of<I>(en);
 #if defined(__CUDA_ARCH__)
-	return hi * c_64k + lo;
+	const u32 a = hd_dp4a(e, 128u << (8 * (I & 3)), 0u) * c_16 + hd_dp4a(m, 128u << (8 * (I & 3)), slt);
+	u32 v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
 #else
-	return lo | (hi << 16);
+	return slt[((m >> (8 * (I & 3))) & 0xffu) + 16u * ((e >> (8 * (I & 3))) & 0xffu)];
 #endif
 }
+// Short line in the HIGH nibble (bytes pre-masked to it): o = 16 o4, e = 16 e4 -> 128 o4 + 2048 e4 = 8 o + 128 e: two IDP.4A
+template <int I> GAI_HDI u32 slt_high(TabRef slt, u64 my, u64 en)
+{
+	const u32 m = half_of<I>(my), e = half_of<I>(en);
+#if defined(__CUDA_ARCH__)
+	const u32 a = hd_dp4a(e, 128u << (8 * (I & 3)), hd_dp4a(m, 8u << (8 * (I & 3)), slt));
+	u32 v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+#else
+	return slt[(((m >> (8 * (I & 3))) & 0xffu) >> 4) + ((e >> (8 * (I & 3))) & 0xffu)];
+#endif
+}
+// field counts of byte J of a bit-plane register, in byte lanes (tpc_entry)
+template <int J> GAI_HDI u32 tpc_of(TabRef tpc, u32 plane)
+{
+#if defined(__CUDA_ARCH__)
+	const u32 a = hd_dp4a(plane, 128u << (8 * J), tpc);
+	u32 v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+#else
+	return tpc[(plane >> (8 * J)) & 0xffu];
+#endif
+}
+GAI_HDI u32 pack16(u32 lo, u32 hi) { return GAI_MADC(hi, c_64k, 65536, lo); }      // lo | hi << 16 (both < 65536) as one IMAD
 
-// phantom masks of the two diagonals sharing byte K (compile time).  D1 byte K: the diagonal r - c = K holds rows K..7
-// (line a), the diagonal r - c = K - 8 rows 0..K-1 (line b).  D2 byte K: r + c = K holds rows 0..K, r + c = K + 8 rows K+1..7.
-template <int K> struct D1Ph { static constexpr u32 a = (1u << K) - 1u, b = (0xffu << K) & 0xffu; static constexpr int len_a = 8 - K, len_b = K; };
-template <int K> struct D2Ph { static constexpr u32 a = (0xffu << (K + 1)) & 0xffu, b = (1u << (K + 1)) - 1u; static constexpr int len_a = K + 1, len_b = 7 - K; };
-
-template <int K> GAI_HDI u32 sweep_r(const Side& my, const Side& en, LutRef lut) { return lut16<K>(lut, my.R, en.R); }
-template <int K> GAI_HDI u32 sweep_c(const Side& my, const Side& en, LutRef lut) { return lut16<K>(lut, my.C, en.C); }
-// The phantom masks are OR-ed into whole registers (4 bytes at a time) before the byte extraction: myA = board | PHA.
-template <template <int> class PH> struct PhWords {
-	static constexpr u64 A = (u64)PH<0>::a | ((u64)PH<1>::a << 8) | ((u64)PH<2>::a << 16) | ((u64)PH<3>::a << 24) | ((u64)PH<4>::a << 32) | ((u64)PH<5>::a << 40) | ((u64)PH<6>::a << 48) | ((u64)PH<7>::a << 56);
-	static constexpr u64 B = (u64)PH<0>::b | ((u64)PH<1>::b << 8) | ((u64)PH<2>::b << 16) | ((u64)PH<3>::b << 24) | ((u64)PH<4>::b << 32) | ((u64)PH<5>::b << 40) | ((u64)PH<6>::b << 48) | ((u64)PH<7>::b << 56);
+// ---- which cells of a diagonal byte belong to which line (compile time).
+// D1 byte K: line a = diagonal r - c = K, rows K..7; line b = diagonal r - c = K - 8, rows 0..K-1.
+// D2 byte K: line a = diagonal r + c = K, rows 0..K; line b = diagonal r + c = K + 8, rows K+1..7.
+// A line of 5+ cells goes to the big LUT with the other line's cells as phantoms (o = e = 1); a line of 2-4 cells sits in
+// one nibble and goes to the short-line table with the rest of ITS nibble as phantoms; a one-cell line has no moves.
+struct DiagConsts { u64 longA, longB, keepLo, phLo, keepHi, phHi; };
+__host__ __device__ constexpr u32 d_first(bool d1, int K, bool a) { return d1 ? (a ? K : 0) : (a ? 0 : K + 1); }          // first row of the line
+__host__ __device__ constexpr u32 d_len(bool d1, int K, bool a) { return d1 ? (a ? 8 - K : K) : (a ? K + 1 : 7 - K); }
+__host__ __device__ constexpr u32 d_cells(bool d1, int K, bool a) { return ((1u << d_len(d1, K, a)) - 1u) << d_first(d1, K, a); }
+__host__ __device__ constexpr DiagConsts make_diag_consts(bool d1)
+{
+	DiagConsts c{0, 0, 0, 0, 0, 0};
+	for (int K = 0; K < 8; ++K) {
+		for (int ab = 0; ab < 2; ++ab) {
+			const bool a = ab == 0;
+			const u32 len = d_len(d1, K, a), cells = d_cells(d1, K, a);
+			if (len >= 5) { (a ? c.longA : c.longB) |= (u64)(0xffu & ~cells) << (8 * K); }
+			else if (len >= 2) {
+				const bool low = d_first(d1, K, a) == 0;                 // short lines start at row 0 or end at row 7
+				if (low) { c.keepLo |= (u64)0x0fu << (8 * K); c.phLo |= (u64)(0x0fu & ~cells) << (8 * K); }
+				else { c.keepHi |= (u64)0xf0u << (8 * K); c.phHi |= (u64)(0xf0u & ~cells) << (8 * K); }
+			}
+		}
+	}
+	return c;
+}
+template <bool D1> struct DiagIn {                        // the pre-masked copies of one rotation (both colours)
+	u64 mA, eA, mB, eB, mLo, eLo, mHi, eHi;
+	GAI_HDI DiagIn(u64 my, u64 en)
+	{
+		constexpr DiagConsts c = make_diag_consts(D1);
+		mA = my | c.longA; eA = en | c.longA; mB = my | c.longB; eB = en | c.longB;
+		mLo = (my & c.keepLo) | c.phLo; eLo = (en & c.keepLo) | c.phLo;
+		mHi = (my & c.keepHi) | c.phHi; eHi = (en & c.keepHi) | c.phHi;
+	}
 };
-template <int K, class PH> GAI_HDI u32 sweep_diag(u64 myA, u64 enA, u64 myB, u64 enB, LutRef lut)
+// the 16-bit move word of diagonal byte K (both lines; their cells are disjoint, so the parts ADD)
+template <bool D1, int K> GAI_HDI u32 sweep_diag(const DiagIn<D1>& d, const SweepTabs& t)
 {
 	u32 v = 0;
-	if (PH::len_a >= 2) v = lut16<K>(lut, myA, enA);       // a one-cell line has no moves
-	if (PH::len_b >= 2) v |= lut16<K>(lut, myB, enB);      // the two lines own disjoint cells
+	bool have = false;
+#define GAI_ACC(x, cname, cval) do { const u32 x_ = (x); v = have ? GAI_MADC(x_, cname, cval, v) : ((cval) == 1 ? x_ : GAI_MADC(x_, cname, cval, 0u)); have = true; } while (0)
+	if (d_len(D1, K, true) >= 5) GAI_ACC(lut16<K>(t.lut, d.mA, d.eA), c_one, 1);
+	if (d_len(D1, K, false) >= 5) GAI_ACC(lut16<K>(t.lut, d.mB, d.eB), c_one, 1);
+	for (int ab = 0; ab < 2; ++ab) {
+		const bool a = ab == 0;
+		const u32 len = d_len(D1, K, a);
+		if (len < 2 || len >= 5) continue;
+		if (d_first(D1, K, a) == 0) GAI_ACC(slt_low<K>(t.slt, d.mLo, d.eLo), c_one, 1);
+		else GAI_ACC(slt_high<K>(t.slt, d.mHi, d.eHi), c_256, 256);       // nibble cells 0-3 are rows 4-7
+	}
+#undef GAI_ACC
 	return v;
 }
+template <int K> GAI_HDI u32 sweep_r(const Side& my, const Side& en, const SweepTabs& t) { return lut16<K>(t.lut, my.R, en.R); }
+template <int K> GAI_HDI u32 sweep_c(const Side& my, const Side& en, const SweepTabs& t) { return lut16<K>(t.lut, my.C, en.C); }
 GAI_HDI u32 rotl16(u32 x, int s)                     // x < 65536, 0 <= s < 16
 {
 	const u32 d = x * 0x10001u;
@@ -97,7 +185,7 @@ struct RowCounts {
 };
 
 // steps 1 + 2.  Every lane executes exactly this straight-line code.
-GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, LutRef lut)
+GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, const SweepTabs& lut)
 {
 	// ---- R lines: all cells of a word lie in one row
 	const u32 r0 = sweep_r<0>(my, en, lut), r1 = sweep_r<1>(my, en, lut), r2 = sweep_r<2>(my, en, lut), r3 = sweep_r<3>(my, en, lut);
@@ -113,18 +201,17 @@ GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, LutRef lut)
 	w[1] = pack16(sweep_c<2>(my, en, lut), sweep_c<3>(my, en, lut));
 	w[2] = pack16(sweep_c<4>(my, en, lut), sweep_c<5>(my, en, lut));
 	w[3] = pack16(sweep_c<6>(my, en, lut), sweep_c<7>(my, en, lut));
-	// D2: cell = row
-	const u64 m2a = my.D2 | PhWords<D2Ph>::A, e2a = en.D2 | PhWords<D2Ph>::A, m2b = my.D2 | PhWords<D2Ph>::B, e2b = en.D2 | PhWords<D2Ph>::B;
-	const u64 m1a = my.D1 | PhWords<D1Ph>::A, e1a = en.D1 | PhWords<D1Ph>::A, m1b = my.D1 | PhWords<D1Ph>::B, e1b = en.D1 | PhWords<D1Ph>::B;
-	w[4] = pack16(sweep_diag<0, D2Ph<0>>(m2a, e2a, m2b, e2b, lut), sweep_diag<1, D2Ph<1>>(m2a, e2a, m2b, e2b, lut));
-	w[5] = pack16(sweep_diag<2, D2Ph<2>>(m2a, e2a, m2b, e2b, lut), sweep_diag<3, D2Ph<3>>(m2a, e2a, m2b, e2b, lut));
-	w[6] = pack16(sweep_diag<4, D2Ph<4>>(m2a, e2a, m2b, e2b, lut), sweep_diag<5, D2Ph<5>>(m2a, e2a, m2b, e2b, lut));
-	w[7] = pack16(sweep_diag<6, D2Ph<6>>(m2a, e2a, m2b, e2b, lut), sweep_diag<7, D2Ph<7>>(m2a, e2a, m2b, e2b, lut));
-	// D1: cell = row as well (word k = (r - c) & 7)
-	w[8] = pack16(sweep_diag<0, D1Ph<0>>(m1a, e1a, m1b, e1b, lut), sweep_diag<1, D1Ph<1>>(m1a, e1a, m1b, e1b, lut));
-	w[9] = pack16(sweep_diag<2, D1Ph<2>>(m1a, e1a, m1b, e1b, lut), sweep_diag<3, D1Ph<3>>(m1a, e1a, m1b, e1b, lut));
-	w[10] = pack16(sweep_diag<4, D1Ph<4>>(m1a, e1a, m1b, e1b, lut), sweep_diag<5, D1Ph<5>>(m1a, e1a, m1b, e1b, lut));
-	w[11] = pack16(sweep_diag<6, D1Ph<6>>(m1a, e1a, m1b, e1b, lut), sweep_diag<7, D1Ph<7>>(m1a, e1a, m1b, e1b, lut));
+	// D2 and D1: cell = row as well (word k = (r + c) & 7 / (r - c) & 7)
+	const DiagIn<false> dg2(my.D2, en.D2);
+	const DiagIn<true> dg1(my.D1, en.D1);
+	w[4] = pack16(sweep_diag<false, 0>(dg2, lut), sweep_diag<false, 1>(dg2, lut));
+	w[5] = pack16(sweep_diag<false, 2>(dg2, lut), sweep_diag<false, 3>(dg2, lut));
+	w[6] = pack16(sweep_diag<false, 4>(dg2, lut), sweep_diag<false, 5>(dg2, lut));
+	w[7] = pack16(sweep_diag<false, 6>(dg2, lut), sweep_diag<false, 7>(dg2, lut));
+	w[8] = pack16(sweep_diag<true, 0>(dg1, lut), sweep_diag<true, 1>(dg1, lut));
+	w[9] = pack16(sweep_diag<true, 2>(dg1, lut), sweep_diag<true, 3>(dg1, lut));
+	w[10] = pack16(sweep_diag<true, 4>(dg1, lut), sweep_diag<true, 5>(dg1, lut));
+	w[11] = pack16(sweep_diag<true, 6>(dg1, lut), sweep_diag<true, 7>(dg1, lut));
 
 	// positional popcount of the 12 registers: carry-save adders on bit planes
 	const FullAdd a0 = fa(w[0], w[1], w[2]), a1 = fa(w[3], w[4], w[5]), a2 = fa(w[6], w[7], w[8]), a3 = fa(w[9], w[10], w[11]);
@@ -134,25 +221,18 @@ GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, LutRef lut)
 	const u32 p2 = t0.s ^ t1.s, d2 = t0.s & t1.s;                                    // twos
 	const FullAdd f4 = fa(t0.c, t1.c, d2);
 	const u32 p4 = f4.s, p8 = f4.c;                                                  // fours, eights   (count <= 12)
-	// fold the two 16-bit halves: (p8 p4 p2 p1)[lo] + (p8 p4 p2 p1)[hi]  -> 5 planes in the low 16 bits
-	const u32 h1 = p1 >> 16, h2 = p2 >> 16, h4 = p4 >> 16, h8 = p8 >> 16;
-	const u32 s1 = p1 ^ h1, k1 = p1 & h1;
-	const FullAdd g2 = fa(p2, h2, k1), g4 = fa(p4, h4, g2.c), g8 = fa(p8, h8, g4.c);
-	const u32 q1 = s1, q2 = g2.s, q4 = g4.s, q8 = g8.s, q16 = g8.c;                  // count <= 24 per (row, sense)
-	// fold the two senses of a cell (even / odd bit of a field): 6 planes on the even bits
-	const u32 M = 0x5555u;
-	const u32 e1 = q1 & M, o1 = (q1 >> 1) & M, e2 = q2 & M, o2 = (q2 >> 1) & M, e4 = q4 & M, o4 = (q4 >> 1) & M;
-	const u32 e8 = q8 & M, o8 = (q8 >> 1) & M, e16 = q16 & M, o16 = (q16 >> 1) & M;
-	const u32 z1 = e1 ^ o1, y1 = e1 & o1;
-	const FullAdd z2 = fa(e2, o2, y1), z4 = fa(e4, o4, z2.c), z8 = fa(e8, o8, z4.c), z16 = fa(e16, o16, z8.c);
-	// spread plane bits (bit 2r) to byte lanes (byte r) and weight them: all on the FMA pipe
-	const u32 SP = 0x00041041u, BM = 0x01010101u;
-#define GAI_SPREAD_LO(x) ((((x) & 0x55u) * SP) & BM)
-#define GAI_SPREAD_HI(x) (((((x) >> 8) & 0x55u) * SP) & BM)
-	tlo += GAI_SPREAD_LO(z1) + GAI_SPREAD_LO(z2.s) * 2u + GAI_SPREAD_LO(z4.s) * 4u + GAI_SPREAD_LO(z8.s) * 8u + GAI_SPREAD_LO(z16.s) * 16u + GAI_SPREAD_LO(z16.c) * 32u;
-	thi += GAI_SPREAD_HI(z1) + GAI_SPREAD_HI(z2.s) * 2u + GAI_SPREAD_HI(z4.s) * 4u + GAI_SPREAD_HI(z8.s) * 8u + GAI_SPREAD_HI(z16.s) * 16u + GAI_SPREAD_HI(z16.c) * 32u;
-#undef GAI_SPREAD_LO
-#undef GAI_SPREAD_HI
+	// The four planes hold, per (16-bit half, row, sense), one bit of a count <= 12.  Per-row totals: every byte of a plane
+	// covers four rows of one half; the field-count table turns it into four byte lanes (popcount of the two sense bits),
+	// weighted by the plane and accumulated -- IDP.4A + LDS + IMAD per byte, nothing on the ALU pipe.
+	const u32 BM = 0x01010101u;
+	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p1), c_one, 1, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p1), c_one, 1, tlo);
+	thi = GAI_MADC(tpc_of<1>(lut.tpc, p1), c_one, 1, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p1), c_one, 1, thi);
+	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p2), c_two, 2, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p2), c_two, 2, tlo);
+	thi = GAI_MADC(tpc_of<1>(lut.tpc, p2), c_two, 2, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p2), c_two, 2, thi);
+	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p4), c_four, 4, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p4), c_four, 4, tlo);
+	thi = GAI_MADC(tpc_of<1>(lut.tpc, p4), c_four, 4, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p4), c_four, 4, thi);
+	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p8), c_eight, 8, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p8), c_eight, 8, tlo);
+	thi = GAI_MADC(tpc_of<1>(lut.tpc, p8), c_eight, 8, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p8), c_eight, 8, thi);
 	rc.plo = tlo * BM;                                   // byte i = rows 0..i   (n <= 96 < 256: no byte overflows)
 	rc.phi = thi * BM + (rc.plo >> 24) * BM;
 	rc.n = rc.phi >> 24;

@@ -52,15 +52,21 @@ static const uint16_t* host_lut()
 	}
 	return lut;
 }
+static loa::SweepTabs host_tabs()
+{
+	static loa::u32 slt[256], tpc[256]; static bool init = false;
+	if (!init) { for (unsigned i = 0; i < 256; ++i) { slt[i] = loa::slt_entry(i); tpc[i] = loa::tpc_entry(i); } init = true; }
+	return loa::sweep_tabs_host(host_lut(), slt, tpc);
+}
 static const loa::SquareTable g_sqt = loa::make_square_table();
 static const loa::DiagTables g_diag = loa::make_diag_tables();
 void host_loa_sweep_movegen_batch(const uint64_t* states, unsigned n, uint8_t* counts, uint8_t* moves)
 {
-	const uint16_t* lut = host_lut();
+	const loa::SweepTabs lut = host_tabs();
 	for (unsigned i = 0; i < n; ++i) {
 		const uint64_t w = states[3 * i], b = states[3 * i + 1]; const unsigned side = (unsigned)states[3 * i + 2] & 1u;
 		const loa::Side my = loa::make_side(side ? b : w, g_sqt.w), en = loa::make_side(side ? w : b, g_sqt.w);
-		const loa::RowCounts rc = loa::sweep_rows(my, en, loa::lut_ref(lut));
+		const loa::RowCounts rc = loa::sweep_rows(my, en, lut);
 		counts[i] = (uint8_t)rc.n;
 		for (unsigned k = 0; k < rc.n && k < 96; ++k) {
 			int from, dir;
@@ -73,7 +79,7 @@ void host_loa_sweep_movegen_batch(const uint64_t* states, unsigned n, uint8_t* c
 void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned max_plies, uint64_t key, uint64_t first_id,
                                   uint8_t* outcome, uint32_t* plies, uint64_t* final_states)
 {
-	const uint16_t* lut = host_lut();
+	const loa::SweepTabs lut = host_tabs();
 	for (unsigned i = 0; i < n; ++i) {
 		unsigned side = (unsigned)states[3 * i + 2] & 1u;
 		loa::Side my = loa::make_side(side ? states[3 * i + 1] : states[3 * i], g_sqt.w), en = loa::make_side(side ? states[3 * i] : states[3 * i + 1], g_sqt.w);
@@ -83,7 +89,7 @@ void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned m
 			const bool c_en = loa::connected_fast(en.R), c_my = loa::connected_fast(my.R);
 			if (c_en | c_my) { out = loa::outcome_of(side ? c_en : c_my, side ? c_my : c_en); break; }
 			if (ply >= max_plies) { out = loa::OUT_CAPPED; break; }
-			const loa::RowCounts rc = loa::sweep_rows(my, en, loa::lut_ref(lut));
+			const loa::RowCounts rc = loa::sweep_rows(my, en, lut);
 			if (rc.n) {
 				if ((ply & 3u) == 0 || ply == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
 				const unsigned idx = gai::choice_index(rnd.v[ply & 3u], rc.n);
