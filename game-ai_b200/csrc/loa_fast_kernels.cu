@@ -201,7 +201,7 @@ __device__ __forceinline__ int wstep_sweep(Side& my, Side& en, FastSim& s, bool 
 	if (phase == 0) rnd = gai::choice_block(key, id, s.ply >> 2);      // warp-uniform branch
 	const u32 idx = gai::choice_index(pick_word(rnd, phase), n);
 	int from, dir;
-	sweep_select(rc, idx, &from, &dir);
+	sweep_select(rc, idx, lut, &from, &dir);
 	if (play) {
 		bool cap = false;
 		if (act) {
@@ -379,7 +379,7 @@ k_movegen_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states,
 		if (live) counts[i] = (uint8_t)cnt;
 		for (u32 k = 0; k < cnt; ++k) {
 			int from, dir;
-			sweep_select(rc, k, &from, &dir);
+			sweep_select(rc, k, tabs, &from, &dir);
 			if (k < GAI_LOA_MAX_MOVES_K) {
 				uint8_t* outp = moves + (size_t)i * 2 * GAI_LOA_MAX_MOVES_K;
 				outp[2 * k] = (uint8_t)from;

@@ -11,8 +11,9 @@
 //              row, so the per-row totals are a POSITIONAL popcount over 24 words:
 //              a carry-save adder tree on bit planes (LOP3 only), whose four planes are turned into byte-lane counts by a
 //              conflict-free per-lane table (FMA pipe + LSU).  A byte-lane prefix sum gives n and the row that holds move idx.
-//   3. piece : inside that row the reference order is by column, then direction: the row's 8 x 8 move bits are
-//              gathered from the line words with shifts and rotations, interleaved, and rank-selected.  No lookups.
+//   3. piece : inside that row the reference order is by column, then direction: the row's fields are gathered from the
+//              line words (one mask per register + IDP.4A), counted per column through the field-count table, and the
+//              one cell that holds the move is rank-selected on its 8 move bits.
 // Move ORDER is the reference's (LinesOfActionZasady.cpp:180-223): ascending square, then W E N S SW NE SE NW.
 #pragma once
 #include "loa_fast.cuh"
@@ -242,19 +243,6 @@ GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, const SweepTabs& lu
 // step 3: the idx-th move (reference order) -> (from, direction).  Straight-line code, no lookups: the moves of
 // the selected row are gathered from the line words (one 2-bit field per column and orientation), interleaved into the
 // reference order (column, then W E | N S | SW NE | SE NW) and rank-selected.
-GAI_HDI u32 spread2to4(u32 x)          // 8 two-bit fields (16 bits) -> 8 nibbles
-{
-	x = (x | (x << 8)) & 0x00ff00ffu;
-	x = (x | (x << 4)) & 0x0f0f0f0fu;
-	x = (x | (x << 2)) & 0x33333333u;
-	return x;
-}
-GAI_HDI u32 spread4to8(u32 x)          // 4 nibbles (16 bits) -> 4 bytes
-{
-	x = (x | (x << 8)) & 0x00ff00ffu;
-	x = (x | (x << 4)) & 0x0f0f0f0fu;
-	return x;
-}
 // Field `row` of each of the 8 words packed two per register in p[0..3] -> one 16-bit word, word j's field at 2-bit
 // position Pj.  M = 0x00030003 << 2*row isolates the field (one LOP3 per register); after that only ONE byte of each
 // 16-bit half is non-zero, so a dp4a with the weight 4^P in both bytes of the half moves the field to position P whatever
@@ -274,7 +262,11 @@ GAI_HDI u32 gather_fields(const u32* p, u32 M, u32 sh4)
 	const u32 hi = gf_acc<P6, P7, true>(m3, gf_acc<P4, P5, true>(m2, gf_acc<P2, P3, true>(m1, gf_acc<P0, P1, true>(m0, 0u))));
 	return (hi * 256u + lo) >> sh4;
 }
-GAI_HDI void sweep_select(const RowCounts& rc, u32 idx, int* from, int* dir)
+// step 3.  Only ONE cell's byte of move bits is ever needed, so the row is not interleaved into 64 bits: the per-column
+// move counts come from the field-count table (8 conflict-free lookups), a byte-lane prefix sum and a SWAR compare give
+// the column, the four 2-bit fields of that column are pulled out with two shifts and two IDP.4A, and the rank-select
+// runs on 8 bits.
+GAI_HDI void sweep_select(const RowCounts& rc, u32 idx, const SweepTabs& t, int* from, int* dir)
 {
 	// row = number of rows whose inclusive prefix is <= idx   (SWAR byte compare, all values < 128)
 	const u32 y = (idx + 1u) * 0x01010101u;
@@ -286,32 +278,36 @@ GAI_HDI void sweep_select(const RowCounts& rc, u32 idx, int* from, int* dir)
 	// R: the row's own word (fields by column: W, E)
 	const u32 rsel = (row & 4u) ? ((row & 2u) ? rc.rp[3] : rc.rp[2]) : ((row & 2u) ? rc.rp[1] : rc.rp[0]);
 	const u32 xr = (rsel >> (16u * (row & 1u))) & 0xffffu;
-	// C: field `row` of column word c -> position c; the field holds (S, N), the reference wants (N, S)
-	const u32 xc0 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 0, M, sh4);
-	const u32 xc = ((xc0 & 0x5555u) << 1) | ((xc0 >> 1) & 0x5555u);
+	// C: field `row` of column word c -> position c  (the field holds (S, N); swapped below, counting does not care)
+	const u32 xc = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 0, M, sh4);
 	// D2: byte k = (row + c) & 7  ->  column c = (k - row) & 7 : gather by k, rotate right by `row` fields
 	const u32 y2 = gather_fields<0, 1, 2, 3, 4, 5, 6, 7>(rc.w + 4, M, sh4);
 	const u32 x2 = rotl16(y2, (int)((16u - sh) & 15u));
 	// D1: byte k = (row - c) & 7 -> column c = (row - k) & 7 : gather reversed ((8-k)&7), rotate left by `row` fields
 	const u32 y1 = gather_fields<0, 7, 6, 5, 4, 3, 2, 1>(rc.w + 8, M, sh4);
 	const u32 x1 = rotl16(y1, (int)sh);
-	// interleave: byte c of z = xr[c] | xc[c] << 2 | x1[c] << 4 | x2[c] << 6
-	const u32 a = spread2to4(xr) | (spread2to4(xc) << 2);          // nibble c = R,C fields
-	const u32 b = spread2to4(x1) | (spread2to4(x2) << 2);          // nibble c = D1,D2 fields
-	const u32 zlo = spread4to8(a & 0xffffu) | (spread4to8(b & 0xffffu) << 4);
-	const u32 zhi = spread4to8(a >> 16) | (spread4to8(b >> 16) << 4);
-	// k-th set bit of (zhi:zlo), branch free
-	const u32 clo = hd_popc(zlo);
-	const bool hi = k >= clo;
-	u32 x = hi ? zhi : zlo; k -= hi ? clo : 0u;
-	int pos = hi ? 32 : 0;
-	{ u32 c = hd_popc(x & 0xffffu); bool g = k >= c; k -= g ? c : 0u; pos += g ? 16 : 0; x = g ? x >> 16 : x;
-	  c = hd_popc(x & 0xffu); g = k >= c; k -= g ? c : 0u; pos += g ? 8 : 0; x = g ? x >> 8 : x;
-	  c = hd_popc(x & 0xfu); g = k >= c; k -= g ? c : 0u; pos += g ? 4 : 0; x = g ? x >> 4 : x;
-	  c = hd_popc(x & 0x3u); g = k >= c; k -= g ? c : 0u; pos += g ? 2 : 0; x = g ? x >> 2 : x;
-	  pos += (k >= (x & 1u)) ? 1 : 0; }
-	*from = (int)(row * 8u) + (pos >> 3);
-	*dir = pos & 7;
+	// moves per column, one byte lane each (<= 8), inclusive prefix sums
+	const u32 A = pack16(xr, xc), B = pack16(x1, x2);
+	u32 cl = tpc_of<0>(t.tpc, A), ch = tpc_of<1>(t.tpc, A);
+	cl = GAI_MADC(tpc_of<2>(t.tpc, A), c_one, 1, cl); ch = GAI_MADC(tpc_of<3>(t.tpc, A), c_one, 1, ch);
+	cl = GAI_MADC(tpc_of<0>(t.tpc, B), c_one, 1, cl); ch = GAI_MADC(tpc_of<1>(t.tpc, B), c_one, 1, ch);
+	cl = GAI_MADC(tpc_of<2>(t.tpc, B), c_one, 1, cl); ch = GAI_MADC(tpc_of<3>(t.tpc, B), c_one, 1, ch);
+	const u32 pl = cl * 0x01010101u, ph = ch * 0x01010101u + (pl >> 24) * 0x01010101u;
+	const u32 yk = (k + 1u) * 0x01010101u;
+	const u32 hlo = ((pl | 0x80808080u) - yk) & 0x80808080u, hhi = ((ph | 0x80808080u) - yk) & 0x80808080u;
+	const u32 col = (u32)(8 - hd_popc(hlo) - hd_popc(hhi)) & 7u;
+	if (col > 0) k -= hd_byte_perm(pl, ph, col - 1u) & 0xffu;
+	// the cell's 8 move bits in reference order: W E | N S | SW NE | SE NW
+	const u32 cs = 2u * col;
+	const u32 fa = (A >> cs) & 0x00030003u, fb = (B >> cs) & 0x00030003u;       // (R, C) and (D1, D2) fields of the column
+	u32 v = hd_dp4a(fb, 0x00400010u, hd_dp4a(fa, 0x00040001u, 0u));              // R | C << 2 | D1 << 4 | D2 << 6
+	v = (v & 0xf3u) | ((v & 4u) << 1) | ((v >> 1) & 4u);                         // C field (S, N) -> (N, S)
+	int pos = 0;
+	{ u32 c = hd_popc(v & 0xfu); bool g = k >= c; k -= g ? c : 0u; pos += g ? 4 : 0; v = g ? v >> 4 : v;
+	  c = hd_popc(v & 0x3u); g = k >= c; k -= g ? c : 0u; pos += g ? 2 : 0; v = g ? v >> 2 : v;
+	  pos += (k >= (v & 1u)) ? 1 : 0; }
+	*from = (int)(row * 8u + col);
+	*dir = pos;
 }
 
 } // namespace loa

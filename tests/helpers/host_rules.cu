@@ -70,7 +70,7 @@ void host_loa_sweep_movegen_batch(const uint64_t* states, unsigned n, uint8_t* c
 		counts[i] = (uint8_t)rc.n;
 		for (unsigned k = 0; k < rc.n && k < 96; ++k) {
 			int from, dir;
-			loa::sweep_select(rc, k, &from, &dir);
+			loa::sweep_select(rc, k, lut, &from, &dir);
 			moves[(size_t)i * 192 + 2 * k] = (uint8_t)from;
 			moves[(size_t)i * 192 + 2 * k + 1] = (uint8_t)loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd);
 		}
@@ -94,7 +94,7 @@ void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned m
 				if ((ply & 3u) == 0 || ply == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
 				const unsigned idx = gai::choice_index(rnd.v[ply & 3u], rc.n);
 				int from, dir;
-				loa::sweep_select(rc, idx, &from, &dir);
+				loa::sweep_select(rc, idx, lut, &from, &dir);
 				const int to = loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd);
 				loa::apply_move_fast(my, en, from, to, g_sqt.w);
 			} else if ((ply & 3u) == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
