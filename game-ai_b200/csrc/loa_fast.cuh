@@ -103,6 +103,25 @@ __host__ __device__ constexpr SquareTable make_square_table()
 	return t;
 }
 
+// line masks by (line type, square): [0] row, [1] column, [2] left diagonal, [3] right diagonal (LinesOfActionZasady.cpp:82-135),
+// and the 8-neighbourhood of every square (:59-81); 2.5 KB, staged into shared memory by the sweep kernels
+struct LineTable { u64 line[4][64]; u64 nbr[64]; };
+__host__ __device__ constexpr LineTable make_line_table()
+{
+	LineTable t{};
+	for (int s = 0; s < 64; ++s) {
+		t.line[0][s] = row_mask(s); t.line[1][s] = col_mask(s); t.line[2][s] = ldiag_mask_slow(s); t.line[3][s] = rdiag_mask_slow(s);
+		const int r = s >> 3, c = s & 7;
+		u64 m = 0;
+		for (int dr = -1; dr <= 1; ++dr) for (int dc = -1; dc <= 1; ++dc) {
+			const int rr = r + dr, cc = c + dc;
+			if ((dr || dc) && rr >= 0 && rr < 8 && cc >= 0 && cc < 8) m |= 1ull << (rr * 8 + cc);
+		}
+		t.nbr[s] = m;
+	}
+	return t;
+}
+
 struct Side { u64 R, C, D1, D2; };      // one colour, four rotations
 
 GAI_HDI u64 bit64(int p) { return 1ull << p; }
@@ -171,6 +190,29 @@ GAI_HDI void apply_move_fast(Side& my, Side& en, int from, int to, const u64* __
 	my.D1 = (my.D1 ^ bit64((hf >> 8) & 63u)) | t1;
 	my.D2 = (my.D2 ^ bit64((hf >> 16) & 63u)) | t2;
 	en.R &= ~tR; en.C &= ~tC; en.D1 &= ~t1; en.D2 &= ~t2;
+}
+
+// target square through the line table: one 8-byte load instead of a branch per line type
+GAI_HDI int move_target_tab(u64 all, int pos, int d, const u64* __restrict__ lines)
+{
+	const u64 L = lines[(d >> 1) * 64 + pos];
+	return pos + (int)hd_popcll(all & L) * dir_step(d);
+}
+// apply_move_fast with the three rotated positions unpacked by IDP.4A (one-byte weight = byte extract on the FMA pipe);
+// returns true when the captured piece (if any) had no neighbour of its own colour -- the only case in which losing it
+// can leave that colour connected: it was a group of its own, so before the capture there were >= 2 groups and every
+// other capture leaves >= 2 (the rest of the victim's group + the untouched ones).
+GAI_HDI bool apply_move_sweep(Side& my, Side& en, int from, int to, const u64* __restrict__ sqt, const u64* __restrict__ nbr)
+{
+	const u32 hf = (u32)(sqt[from] >> 32), ht = (u32)(sqt[to] >> 32);
+	const u64 tR = bit64(to), tC = bit64((int)hd_dp4a(ht, 0x00000001u, 0u)), t1 = bit64((int)hd_dp4a(ht, 0x00000100u, 0u)), t2 = bit64((int)hd_dp4a(ht, 0x00010000u, 0u));
+	const bool cap = (en.R & tR) != 0;
+	my.R = (my.R ^ bit64(from)) | tR;
+	my.C = (my.C ^ bit64((int)hd_dp4a(hf, 0x00000001u, 0u))) | tC;
+	my.D1 = (my.D1 ^ bit64((int)hd_dp4a(hf, 0x00000100u, 0u))) | t1;
+	my.D2 = (my.D2 ^ bit64((int)hd_dp4a(hf, 0x00010000u, 0u))) | t2;
+	en.R &= ~tR; en.C &= ~tC; en.D1 &= ~t1; en.D2 &= ~t2;
+	return cap && (en.R & nbr[to]) == 0;
 }
 
 } // namespace loa

@@ -9,15 +9,16 @@ namespace loa {
 
 __constant__ DiagTables c_diag2 = make_diag_tables();
 __constant__ SquareTable c_sqt = make_square_table();
+__constant__ LineTable c_lines = make_line_table();
 
 struct FastSmem {
-	const uint16_t* lut; const u64* sqt; const u64* ld; const u64* rd; const u32* slt; const u32* tpc;
+	const uint16_t* lut; const u64* sqt; const u64* lines; const u64* ld; const u64* rd; const u64* nbr; const u32* slt; const u32* tpc;
 };
 
-// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][64 x u64 ld][64 x u64 rd][tail]
+// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][4 x 64 x u64 line masks: row, column, ld, rd][64 x u64 neighbourhoods][tail]
 //   tail of the static-sweep kernels : [256 x 32 lanes x u32 short-line table][256 x 32 x u32 field-count table]
 //   tail of the per-piece kernels    : [16 x 1024 bytes piece squares]
-constexpr int FAST_SQ_OFF = LUT_BYTES + 3 * 64 * 8;
+constexpr int FAST_SQ_OFF = LUT_BYTES + 6 * 64 * 8;
 constexpr int FAST_SMEM_BYTES = FAST_SQ_OFF + 16 * 1024;
 constexpr int SWEEP_SMEM_BYTES = FAST_SQ_OFF + 2 * 256 * 32 * 4;
 
@@ -28,8 +29,11 @@ __device__ __forceinline__ FastSmem load_fast_smem(unsigned char* smem, const ui
 	uint4* d = reinterpret_cast<uint4*>(smem);
 	for (int i = threadIdx.x; i < LUT_BYTES / 16; i += blockDim.x) d[i] = __ldg(g_lut + i);
 	u64* sq = reinterpret_cast<u64*>(smem + LUT_BYTES);
-	for (int i = threadIdx.x; i < 64; i += blockDim.x) { sq[i] = c_sqt.w[i]; sq[64 + i] = c_diag2.ld[i]; sq[128 + i] = c_diag2.rd[i]; }
-	FastSmem f; f.lut = reinterpret_cast<const uint16_t*>(smem); f.sqt = sq; f.ld = sq + 64; f.rd = sq + 128;
+	for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+		sq[i] = c_sqt.w[i]; sq[320 + i] = c_lines.nbr[i];
+		sq[64 + i] = c_lines.line[0][i]; sq[128 + i] = c_lines.line[1][i]; sq[192 + i] = c_lines.line[2][i]; sq[256 + i] = c_lines.line[3][i];
+	}
+	FastSmem f; f.lut = reinterpret_cast<const uint16_t*>(smem); f.sqt = sq; f.lines = sq + 64; f.ld = sq + 192; f.rd = sq + 256; f.nbr = sq + 320;
 	f.slt = f.tpc = nullptr;
 	if (SWEEP_TABLES) {
 		u32* t = reinterpret_cast<u32*>(smem + FAST_SQ_OFF);
@@ -205,9 +209,8 @@ __device__ __forceinline__ int wstep_sweep(Side& my, Side& en, FastSim& s, bool 
 	if (play) {
 		bool cap = false;
 		if (act) {
-			const int to = move_target(my.R | en.R, from, dir, f.ld, f.rd);
-			cap = (en.R >> to) & 1ull;
-			apply_move_fast(my, en, from, to, f.sqt);
+			const int to = move_target_tab(my.R | en.R, from, dir, f.lines);
+			cap = apply_move_sweep(my, en, from, to, f.sqt, f.nbr);       // true only if the victim was a group of its own
 		}
 		s.side ^= 1u;
 		s.ply += 1;

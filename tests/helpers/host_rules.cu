@@ -60,6 +60,7 @@ static loa::SweepTabs host_tabs()
 }
 static const loa::SquareTable g_sqt = loa::make_square_table();
 static const loa::DiagTables g_diag = loa::make_diag_tables();
+static const loa::LineTable g_lines = loa::make_line_table();
 void host_loa_sweep_movegen_batch(const uint64_t* states, unsigned n, uint8_t* counts, uint8_t* moves)
 {
 	const loa::SweepTabs lut = host_tabs();
@@ -85,8 +86,9 @@ void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned m
 		loa::Side my = loa::make_side(side ? states[3 * i + 1] : states[3 * i], g_sqt.w), en = loa::make_side(side ? states[3 * i] : states[3 * i + 1], g_sqt.w);
 		unsigned ply = 0; int out = -1;
 		gai::Philox4 rnd{};
+		bool chk_en = true, chk_my = true;
 		for (;;) {
-			const bool c_en = loa::connected_fast(en.R), c_my = loa::connected_fast(my.R);
+			const bool c_en = chk_en && loa::connected_fast(en.R), c_my = chk_my && loa::connected_fast(my.R);
 			if (c_en | c_my) { out = loa::outcome_of(side ? c_en : c_my, side ? c_my : c_en); break; }
 			if (ply >= max_plies) { out = loa::OUT_CAPPED; break; }
 			const loa::RowCounts rc = loa::sweep_rows(my, en, lut);
@@ -95,9 +97,11 @@ void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned m
 				const unsigned idx = gai::choice_index(rnd.v[ply & 3u], rc.n);
 				int from, dir;
 				loa::sweep_select(rc, idx, lut, &from, &dir);
-				const int to = loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd);
-				loa::apply_move_fast(my, en, from, to, g_sqt.w);
-			} else if ((ply & 3u) == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
+				const int to = loa::move_target_tab(my.R | en.R, from, dir, &g_lines.line[0][0]);
+				if (to != loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd)) { out = 0xee; break; }
+				chk_my = loa::apply_move_sweep(my, en, from, to, g_sqt.w, g_lines.nbr);
+				chk_en = true;
+			} else { chk_en = false; chk_my = false; if ((ply & 3u) == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2); }
 			const loa::Side t = my; my = en; en = t;
 			side ^= 1u; ++ply;
 		}

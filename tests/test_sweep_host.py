@@ -23,7 +23,7 @@ def test_sweep_movegen_on_host_vs_oracle(hostlib, oracle):
 
 
 def test_sweep_playouts_on_host_vs_oracle(hostlib, oracle):
-    S = corpus(oracle, 1500, 0xA11CE)
+    S = corpus(oracle, 6000, 0xA11CE)
     n = len(S)
     for cap in (50000, 37):
         o = np.zeros(n, np.uint8); pl = np.zeros(n, np.uint32); f = np.zeros((n, 3), np.uint64)
