@@ -308,7 +308,7 @@ def main():
                 "config": {"workload": "LOA leaf-parallel rollouts: %d reachable leaves x %d playouts/leaf per GPU to game end (max_plies %d)" % (n, ppl, MAX_PLIES),
                            "leaves_per_gpu": n, "playouts_per_leaf": ppl, "max_plies": MAX_PLIES, "philox_key": SEED,
                            "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "leaf/root-parallel x%d, no data-path collective" % world,
-                           "threads_per_block": args.threads_per_block or [256, 1024, 768][args.rules_impl],
+                           "threads_per_block": eng.launch_config()["threads_per_block"], "plies_per_loop_trip": eng.launch_config()["plies_per_trip"],
                            "kernel": ["k_rollout (bitboard baseline)", "k_rollout_fast<per-piece> (rotated boards + line LUT)", "k_rollout_fast<sweep> (static line sweep + CSA row counts)"][args.rules_impl], "device": info["name"]},
                 "kernel_ms_per_step": kern_ms / args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps,
                 "playouts_per_step": all_playouts // args.steps, "mean_plies_per_playout": mean_plies, "plies_per_sec": all_plies / (dev_ms * 1e-3),

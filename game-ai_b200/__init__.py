@@ -63,6 +63,7 @@ def lib():
         L.gai_sync.argtypes = [_vp]
         L.gai_get_device_info.argtypes = [_vp, _vp]
         L.gai_set_launch_config.argtypes = [_vp, _i32, _i32]
+        L.gai_get_launch_config.argtypes = [_vp, _vp, _vp]
         L.gai_set_rules_impl.argtypes = [_vp, _i32]
         L.gai_loa_movegen.argtypes = [_vp, _vp, _u32, _vp, _vp]
         L.gai_loa_apply.argtypes = [_vp, _vp, _vp, _u32, _vp]
@@ -167,6 +168,11 @@ class GpuRollout:
 
     def set_launch_config(self, threads_per_block=0, blocks_per_sm=0):
         self._ck(self.L.gai_set_launch_config(self.h, threads_per_block, blocks_per_sm))
+
+    def launch_config(self):
+        t, u = ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self.L.gai_get_launch_config(self.h, ctypes.byref(t), ctypes.byref(u)))
+        return {"threads_per_block": t.value, "plies_per_trip": u.value}
 
     def set_rules_impl(self, impl):
         """0 = bitboard baseline kernels, 1 = rotated boards + line LUT per piece, 2 = static line sweep."""

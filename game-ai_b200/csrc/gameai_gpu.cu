@@ -45,7 +45,7 @@ struct gai_ctx {
 	int threads = 256, blocks_per_sm = 4;   // baseline kernel launch shape
 	int impl = 2;                           // 0 = bitboard rules (loa_rules.cuh), 1 = rotated boards + line LUT per piece (loa_fast.cuh), 2 = static line sweep (loa_sweep.cuh)
 	int fast_threads = 1024;                // one CTA per SM for the LUT kernels
-	int sweep_threads = 768;                // the static-sweep kernel keeps 28 line words live: 78 registers -> 768 threads
+	int sweep_threads = 896;                // the static-sweep kernel fits 72 registers without spilling: 28 warps per SM
 	int sweep_unroll = 2;                   // plies per loop trip of the static-sweep kernel (1, 2, 4); GAI_SWEEP_UNROLL overrides
 	void* d_lut = nullptr;
 	// scratch
@@ -165,7 +165,7 @@ int gai_create(int device, gai_ctx** out)
 	if (device < 0 || device >= count) return fail(nullptr, GAI_ERR_INVALID, "gai_create: device ordinal out of range");
 	gai_ctx* ctx = new gai_ctx();
 	if (const char* u = getenv("GAI_SWEEP_UNROLL")) { const int v = atoi(u); if (v == 1 || v == 2 || v == 4) ctx->sweep_unroll = v; }      // tuning knob
-	if (const char* u = getenv("GAI_SWEEP_THREADS")) { const int v = atoi(u); if (v == 512 || v == 768 || v == 1024) ctx->sweep_threads = v; }
+	if (const char* u = getenv("GAI_SWEEP_THREADS")) { const int v = atoi(u); if (v >= 512 && v <= 1024 && v % 128 == 0) ctx->sweep_threads = v; }
 	ctx->err[0] = 0;
 	ctx->device = device;
 	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
@@ -250,6 +250,14 @@ int gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm
 }
 
 uint64_t gai_launch_count(const gai_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gai_get_launch_config(gai_ctx* ctx, int* threads_per_block, int* plies_per_trip)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (threads_per_block) *threads_per_block = ctx->impl == 2 ? ctx->sweep_threads : ctx->impl == 1 ? ctx->fast_threads : ctx->threads;
+	if (plies_per_trip) *plies_per_trip = ctx->impl == 2 ? ctx->sweep_unroll : 1;
+	return GAI_OK;
+}
 
 int gai_set_rules_impl(gai_ctx* ctx, int impl)
 {

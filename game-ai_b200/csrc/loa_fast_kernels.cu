@@ -461,7 +461,7 @@ cudaError_t loa_fast_prepare()
 	cudaError_t e;
 	if ((e = cudaFuncSetAttribute(k_rollout_fast<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 #define GAI_PREP(T, U) if ((e = cudaFuncSetAttribute(k_rollout_fast<true, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
-	GAI_PREP(1024, 1) GAI_PREP(768, 1) GAI_PREP(512, 1) GAI_PREP(1024, 2) GAI_PREP(768, 2) GAI_PREP(512, 2) GAI_PREP(1024, 4) GAI_PREP(768, 4) GAI_PREP(512, 4)
+	GAI_PREP(1024, 1) GAI_PREP(768, 1) GAI_PREP(512, 1) GAI_PREP(1024, 2) GAI_PREP(896, 2) GAI_PREP(768, 2) GAI_PREP(640, 2) GAI_PREP(512, 2) GAI_PREP(1024, 4) GAI_PREP(768, 4) GAI_PREP(512, 4)
 #undef GAI_PREP
 	if ((e = cudaFuncSetAttribute(k_movegen_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_movegen_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
@@ -489,7 +489,7 @@ void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint
 #define GAI_RL_T(U) do { if (threads > 768) GAI_RL(1024, U); else if (threads > 512) GAI_RL(768, U); else GAI_RL(512, U); } while (0)
 	if (!sweep) k_rollout_fast<false, 1024, 1><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
 	else if (sweep >= 4) GAI_RL_T(4);
-	else if (sweep >= 2) GAI_RL_T(2);
+	else if (sweep >= 2) { if (threads > 896) GAI_RL(1024, 2); else if (threads > 768) GAI_RL(896, 2); else if (threads > 640) GAI_RL(768, 2); else if (threads > 512) GAI_RL(640, 2); else GAI_RL(512, 2); }
 	else GAI_RL_T(1);
 #undef GAI_RL_T
 #undef GAI_RL

@@ -29,6 +29,11 @@ namespace loa {
 // Multipliers read from the constant bank: ptxas cannot strength-reduce  x * c[..] + y  into LEA / SHF / LOP3 (ALU pipe),
 // it stays an IMAD.
 __constant__ u32 c_one = 1, c_two = 2, c_four = 4, c_eight = 8, c_14 = 14, c_16 = 16, c_256 = 256, c_64k = 65536;
+// dp4a weights (a byte weight in byte position k).  IDP.4A takes its weight from a uniform register; kept together in the
+// constant bank they arrive four per LDCU.128 instead of one UMOV each.
+struct WeightTab { u32 w37[4], w2[4], w128[4], w8[4]; };
+__constant__ WeightTab c_wt = { { 37u, 37u << 8, 37u << 16, 37u << 24 }, { 2u, 2u << 8, 2u << 16, 2u << 24 },
+                                { 128u, 128u << 8, 128u << 16, 128u << 24 }, { 8u, 8u << 8, 8u << 16, 8u << 24 } };
 #if defined(__CUDA_ARCH__)
 typedef u32 LutRef;                                   // shared-memory byte address of the line LUT
 typedef u32 TabRef;                                   // shared-memory byte address of a per-lane table, this lane's column
@@ -64,7 +69,7 @@ template <int I> GAI_HDI u32 lut16(LutRef lut, u64 my, u64 en)          // LUT w
 {
 	const u32 m = half_of<I>(my), e = half_of<I>(en);
 #if defined(__CUDA_ARCH__)
-	const u32 a = hd_dp4a(e, 37u << (8 * (I & 3)), 0u) * c_14 + hd_dp4a(m, 2u << (8 * (I & 3)), lut);
+	const u32 a = hd_dp4a(e, c_wt.w37[I & 3], 0u) * c_14 + hd_dp4a(m, c_wt.w2[I & 3], lut);
 	u32 v;
 	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
@@ -78,7 +83,7 @@ template <int I> GAI_HDI u32 slt_low(TabRef slt, u64 my, u64 en)
 {
 	const u32 m = half_of<I>(my), e = half_of<I>(en);
 #if defined(__CUDA_ARCH__)
-	const u32 a = hd_dp4a(e, 128u << (8 * (I & 3)), 0u) * c_16 + hd_dp4a(m, 128u << (8 * (I & 3)), slt);
+	const u32 a = hd_dp4a(e, c_wt.w128[I & 3], 0u) * c_16 + hd_dp4a(m, c_wt.w128[I & 3], slt);
 	u32 v;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
@@ -91,7 +96,7 @@ template <int I> GAI_HDI u32 slt_high(TabRef slt, u64 my, u64 en)
 {
 	const u32 m = half_of<I>(my), e = half_of<I>(en);
 #if defined(__CUDA_ARCH__)
-	const u32 a = hd_dp4a(e, 128u << (8 * (I & 3)), hd_dp4a(m, 8u << (8 * (I & 3)), slt));
+	const u32 a = hd_dp4a(e, c_wt.w128[I & 3], hd_dp4a(m, c_wt.w8[I & 3], slt));
 	u32 v;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
@@ -103,7 +108,7 @@ template <int I> GAI_HDI u32 slt_high(TabRef slt, u64 my, u64 en)
 template <int J> GAI_HDI u32 tpc_of(TabRef tpc, u32 plane)
 {
 #if defined(__CUDA_ARCH__)
-	const u32 a = hd_dp4a(plane, 128u << (8 * J), tpc);
+	const u32 a = hd_dp4a(plane, c_wt.w128[J], tpc);
 	u32 v;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;

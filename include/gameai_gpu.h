@@ -74,10 +74,13 @@ int  gai_get_device_info(gai_ctx* ctx, gai_device_info* info);
 int  gai_sync(gai_ctx* ctx);
 /* rollout kernel launch shape: threads per block, blocks per SM (0 = keep default). */
 int  gai_set_launch_config(gai_ctx* ctx, int threads_per_block, int blocks_per_sm);
+/* launch shape the rollout entry points use for the selected rules formulation: threads per block and, for the static
+ * sweep, the number of plies per loop trip (either pointer may be NULL). */
+int  gai_get_launch_config(gai_ctx* ctx, int* threads_per_block, int* plies_per_trip);
 /* Which device formulation of the rules the sweep and rollout entry points use.  Both give identical results
  * (tests run all three): 0 = per-piece 64-bit bitboard restatement (baseline), 1 = rotated boards + shared-memory
  * line LUT, one piece at a time, 2 = static sweep over the 32 line bytes with carry-save row counts (default; one CTA
- * of 768 threads per SM). */
+ * of 896 threads per SM). */
 int  gai_set_rules_impl(gai_ctx* ctx, int impl);
 /* number of kernel launches issued through ctx since creation (bench.py's gpu_launches) */
 uint64_t gai_launch_count(const gai_ctx* ctx);
