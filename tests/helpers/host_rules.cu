@@ -35,6 +35,8 @@ int host_pan_terminal(int np, const uint64_t* st, int* score, int* ev0, int* ev1
 }
 // LOA line LUT: entry for own/enemy occupancy bytes, and the per-square rotation constants
 int host_loa_lut_entry(unsigned o, unsigned e) { return loa::lut_entry(o, e); }
+unsigned host_loa_slt_entry(unsigned i) { return loa::slt_entry(i); }
+unsigned host_loa_tpc_entry(unsigned b) { return loa::tpc_entry(b); }
 int host_loa_pos_c(int s) { return loa::pos_c(s); }
 int host_loa_pos_d1(int s) { return loa::pos_d1(s); }
 int host_loa_pos_d2(int s) { return loa::pos_d2(s); }

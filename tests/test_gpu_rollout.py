@@ -63,13 +63,37 @@ def test_rollout_independent_of_launch_shape(gpu, oracle):
     """Playout identity is (leaf, playout) -> Philox counter, never the lane: any launch shape, same counts."""
     S = oracle.gen_reachable(3000, 77)
     ref_counts, ref_st = gpu.rollout(S, 5, 50000, 3, 0)
-    for tpb, bps in ((32, 1), (64, 3), (128, 8), (256, 2), (512, 1), (1024, 1)):
+    default = gpu.launch_config()["threads_per_block"]
+    for tpb, bps in ((32, 1), (64, 3), (128, 8), (256, 2), (512, 1), (640, 1), (768, 1), (896, 1), (1024, 1)):
         gpu.set_launch_config(tpb, bps)
+        assert gpu.launch_config()["threads_per_block"] == (tpb if gpu.impl else min(tpb, 256))
         counts, st = gpu.rollout(S, 5, 50000, 3, 0)
         assert (counts == ref_counts).all() and st["plies"] == ref_st["plies"]
-    gpu.set_launch_config(1024, 4)
+    gpu.set_launch_config(default, 4)
     oc, oplies = oracle.rollout_states(S[:500], 5, 50000, 3, 0)
     assert (ref_counts[:500] == oc).all()
+
+
+def test_sweep_kernel_unroll_variants(oracle):
+    """The static-sweep kernel with 1, 2 and 4 plies per loop trip (GAI_SWEEP_UNROLL, read at gai_create): same playouts."""
+    import os
+    import gameai_b200 as g
+    S = oracle.gen_reachable(4000, 91)
+    oc, oplies = oracle.rollout_states(S[:600], 3, 50000, 11, 5)
+    ref = None
+    try:
+        for u in ("1", "2", "4"):
+            os.environ["GAI_SWEEP_UNROLL"] = u
+            eng = g.GpuRollout(0)
+            assert eng.launch_config()["plies_per_trip"] == int(u)
+            counts, st = eng.rollout(S, 3, 50000, 11, 5)
+            eng.close()
+            assert (counts[:600] == oc).all()
+            if ref is None:
+                ref = (counts, st["plies"])
+            assert (counts == ref[0]).all() and st["plies"] == ref[1]
+    finally:
+        os.environ.pop("GAI_SWEEP_UNROLL", None)
 
 
 def test_device_resident_path_matches_host_path(gpu, oracle):

@@ -32,3 +32,30 @@ def test_sweep_playouts_on_host_vs_oracle(hostlib, oracle):
         oo, opl, of = oracle.playout_trace_batch(S, cap, 0xBEEF, 1000)
         assert (o == oo).all() and (pl == opl).all()
         assert (f[:, :2] == of[:, :2]).all() and ((f[:, 2] & 1) == (of[:, 2] & 1)).all()
+
+
+def test_small_tables_by_definition(hostlib):
+    """The two per-lane tables of the sweep kernel (loa_fast.cuh slt_entry / tpc_entry) against their definitions: the
+    short-line table is the line LUT restricted to four cells (cells 4-7 walls), the field-count table the popcount of
+    each 2-bit field in its own byte lane."""
+    hostlib.host_loa_lut_entry.restype = ctypes.c_int
+    hostlib.host_loa_slt_entry.restype = ctypes.c_uint
+    hostlib.host_loa_tpc_entry.restype = ctypes.c_uint
+    for idx in range(256):
+        o4, e4 = idx & 15, idx >> 4
+        assert hostlib.host_loa_slt_entry(idx) == hostlib.host_loa_lut_entry(o4 | 0xf0, e4 | 0xf0) & 0xff
+        t = hostlib.host_loa_tpc_entry(idx)
+        assert [(t >> (8 * j)) & 0xff for j in range(4)] == [bin((idx >> (2 * j)) & 3).count("1") for j in range(4)]
+    # a 4-cell line with no phantoms equals the 8-cell line whose upper four cells are walls: same moves as an edge row
+    for o4 in range(16):
+        for e4 in range(16):
+            if o4 & e4:
+                continue
+            full = hostlib.host_loa_lut_entry(o4, e4)       # cells 4-7 EMPTY: pieces may run past cell 3
+            short = hostlib.host_loa_slt_entry(o4 | (e4 << 4))
+            n = bin(o4 | e4).count("1")
+            for p in range(4):
+                up_full = (full >> (2 * p + 1)) & 1
+                up_short = (short >> (2 * p + 1)) & 1
+                assert up_short == (up_full if p + n < 4 else 0)
+                assert ((short >> (2 * p)) & 1) == ((full >> (2 * p)) & 1)
