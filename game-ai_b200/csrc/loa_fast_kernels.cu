@@ -268,6 +268,8 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 	const FastSmem f = load_fast_smem<SWEEP>(smem, g_lut);
 
 	const u64 total = (u64)n_leaves * ppl;
+	const bool ppl_pow2 = (ppl & (ppl - 1u)) == 0;
+	const u32 ppl_shift = (u32)__ffs((int)ppl) - 1u;
 	const u32 lane = threadIdx.x & 31u;
 	FastSim s; gai::Philox4 rnd;
 	u64 item = 0, pid = 0; u32 leaf = 0;
@@ -289,14 +291,13 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 				item = base + __popc(needmask & ((1u << lane) - 1u));
 				if (item >= total) exhausted = true;
 				else {
-					const u32 slot = (u32)(item / ppl);
+					const u32 slot = ppl_pow2 ? (u32)(item >> ppl_shift) : (u32)(item / ppl);      // warp-uniform: no division for 2^k playouts per leaf
 					leaf = __ldg(order + slot);
 					pid = first_id + (u64)leaf * ppl + (item - (u64)slot * ppl);       // identity = (leaf, playout), not the schedule
-					const ulonglong2* lp = prep + 4 * (size_t)leaf;       // four 16-byte loads per playout
-					const ulonglong2 w0 = __ldg(lp), w1 = __ldg(lp + 1), b0 = __ldg(lp + 2), b1 = __ldg(lp + 3);
 					const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
-					const Side W = Side{w0.x, w0.y, w1.x, w1.y}, B = Side{b0.x, b0.y, b1.x, b1.y};
-					s.side = side; s.my = side ? B : W; s.en = side ? W : B;
+					const ulonglong2* lp = prep + 4 * (size_t)leaf;       // four 16-byte loads per playout: {white R C, white D1 D2, black R C, black D1 D2}
+					const ulonglong2 m0 = __ldg(lp + 2 * side), m1 = __ldg(lp + 2 * side + 1), e0 = __ldg(lp + 2 * (side ^ 1u)), e1 = __ldg(lp + 2 * (side ^ 1u) + 1);
+					s.side = side; s.my = Side{m0.x, m0.y, m1.x, m1.y}; s.en = Side{e0.x, e0.y, e1.x, e1.y};
 					s.ply = 0; s.rq = 0xffffffffu; s.chk_en = true; s.chk_my = true;
 					need = false;
 				}
