@@ -584,7 +584,7 @@ int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves
 	CU(cudaSetDevice(ctx->device));
 	const size_t sb = (size_t)n_leaves * 40, rb = (size_t)n_leaves * sizeof(gai_pan_result);
 	EN(ctx->h_in, sb, true); EN(ctx->h_out, rb, true);
-	EN(ctx->d_in, sb, false); EN(ctx->d_out, rb, false); EN(ctx->d_misc, 64, false);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, rb, false); EN(ctx->d_misc, 64, false); EN(ctx->d_prep, (size_t)n_leaves * 32, false);
 	memcpy(ctx->h_in.p, leaves, sb);
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 	CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -594,9 +594,9 @@ int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves
 	int blocks = ctx->prop.multiProcessorCount * 8;
 	if ((total + 255) / 256 < (uint64_t)blocks) blocks = (int)((total + 255) / 256);
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-	launch_pan_rollout(ctx->d_in.p, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, (uint32_t*)ctx->d_out.p,
+	launch_pan_rollout(ctx->d_in.p, ctx->d_prep.p, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, (uint32_t*)ctx->d_out.p,
 	                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2, PAN_BAD_PTR, blocks, ctx->stream);
-	LAUNCHED("k_pan_rollout");
+	LAUNCHED("k_pan_prepare"); LAUNCHED("k_pan_rollout");
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	uint32_t bad = 0;
 	CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));

@@ -39,5 +39,6 @@ void launch_pan_apply(const void* d_states, const uint64_t* d_mv, uint32_t n, in
 void launch_pan_terminal(const void* d_states, uint32_t n, int np, uint8_t* d_term, int* d_score, int* d_ev0, int* d_ev1, uint32_t* d_bad, cudaStream_t st);
 void launch_pan_playout_trace(const void* d_states, uint32_t n, int np, uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id,
                               uint8_t* d_code, uint32_t* d_plies, int* d_value, void* d_final, uint32_t* d_bad, cudaStream_t st);
-void launch_pan_rollout(const void* d_states, uint32_t n_leaves, int np, uint32_t ppl, uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id,
+// (also launches k_pan_prepare: 40-byte reference states -> 32-byte device records in d_prep, n_leaves x 32 B)
+void launch_pan_rollout(const void* d_states, void* d_prep, uint32_t n_leaves, int np, uint32_t ppl, uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id,
                         uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter, uint32_t* d_bad, int blocks, cudaStream_t st);
