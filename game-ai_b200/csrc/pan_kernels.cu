@@ -250,7 +250,8 @@ void launch_pan_rollout(const void* d_states, void* d_prep, uint32_t n_leaves, i
 	// games: 2.6x; two players: +29 %); with three or four players and the reference's playout_depth of 50 nearly every
 	// playout runs into the cap, divergence is bounded, and the lane-independent loop (no refill cadence) is 11-17 % faster
 	// (profiles/r01_pan_bench.json).  GAI_PAN_KERNEL=0/1 forces one of them.
-	static const int forced = [] { const char* e = getenv("GAI_PAN_KERNEL"); return e ? atoi(e) : -1; }();
+	const char* fe = getenv("GAI_PAN_KERNEL");
+	const int forced = fe && *fe ? atoi(fe) : -1;
 	const int variant = forced >= 0 ? forced : (max_plies <= 64 && np >= 3) ? 0 : 1;
 	if (variant == 0) k_pan_rollout_indep<<<blocks, 256, 0, st>>>((const uint4*)d_prep, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, d_out, (u64*)d_stats, d_counter, d_bad);
 	else k_pan_rollout<<<blocks, 256, 0, st>>>((const uint4*)d_prep, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, d_out, (u64*)d_stats, d_counter, d_bad);

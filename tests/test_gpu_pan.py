@@ -102,3 +102,22 @@ def test_determinized_views_roll_out(gpu, po):
     r, st = gpu.pan_rollout(npl, D, 8, 50, 1, 77, 0)
     orr, oplies = po.playout_batch(npl, D, 8, 50, 1, 77, 0)
     assert (r == orr).all() and st["plies"] == oplies
+
+
+def test_both_rollout_kernels_agree(gpu, po):
+    """The lane-independent and the warp-synchronous Pan rollout kernel (GAI_PAN_KERNEL=0/1, normally chosen by ply cap and
+    player count) give the same per-deal results, capped and uncapped, and both match the oracle."""
+    import os
+    try:
+        for npl, cap in ((2, 50), (3, 50), (4, 1000)):
+            S = po.gen_reachable(npl, 3000, 99 + npl, 60)
+            got = []
+            for v in ("0", "1"):
+                os.environ["GAI_PAN_KERNEL"] = v
+                r, st = gpu.pan_rollout(npl, S, 4, cap, 1, 21, 1000)
+                got.append((r, st["plies"], st["playouts"]))
+            assert (got[0][0] == got[1][0]).all() and got[0][1:] == got[1][1:]
+            orr, oplies = po.playout_batch(npl, S[:500], 4, cap, 1, 21, 1000)
+            assert (orr == got[1][0][:500]).all()
+    finally:
+        os.environ.pop("GAI_PAN_KERNEL", None)
