@@ -17,37 +17,49 @@ struct GameState { uint64_t white, black, current_player; };      // only bit 0 
 
 namespace {
 
-inline bool on_board(int r, int c) { return (unsigned)r < 8u && (unsigned)c < 8u; }
+// line masks through every square: [0] row (step 1), [1] column (step 8), [2] diagonal A1->H8 (step 9), [3] diagonal H1->A8 (step 7)
+// (LinesOfActionZasady.cpp:82-135); the MCTS player's host tree calls GetPlayerLegalMoves once per expanded node
+struct LineMasks {
+	uint64_t m[4][64];
+	LineMasks()
+	{
+		for (int p = 0; p < 64; ++p) {
+			const int r = p >> 3, c = p & 7;
+			uint64_t row = 0, col = 0, ld = 0, rd = 0;
+			for (int k = 0; k < 8; ++k) {
+				row |= 1ull << (r * 8 + k); col |= 1ull << (k * 8 + c);
+				const int r1 = k + (r - c), r2 = (r + c) - k;                  // column k of the two diagonals
+				if (r1 >= 0 && r1 < 8) ld |= 1ull << (r1 * 8 + k);
+				if (r2 >= 0 && r2 < 8) rd |= 1ull << (r2 * 8 + k);
+			}
+			m[0][p] = row; m[1][p] = col; m[2][p] = ld; m[3][p] = rd;
+		}
+	}
+};
+const LineMasks g_lines;
 
-// number of pieces on the line through (r,c) in direction (dr,dc), both senses
-inline int line_count(uint64_t all, int r, int c, int dr, int dc)
+// the two moves of the piece on `pos` along one line: distance = pieces of both colours on the line (:191-192); the target
+// must be on the line and not an own piece (:142), and no ENEMY piece may stand strictly between (:146-148)
+inline void line_moves(uint64_t mine, uint64_t theirs, uint64_t L, int step, int pos, bool up_first, Move* out, int& n)
 {
-	int n = 0;
-	for (int k = -7; k <= 7; ++k) { const int rr = r + dr * k, cc = c + dc * k; if (on_board(rr, cc) && (all >> (rr * 8 + cc) & 1)) ++n; }
-	return n;
-}
-inline void try_move(uint64_t mine, uint64_t theirs, int r, int c, int dr, int dc, int dist, Move* out, int& n)
-{
-	const int tr = r + dr * dist, tc = c + dc * dist;
-	if (!on_board(tr, tc) || (mine >> (tr * 8 + tc) & 1)) return;
-	for (int k = 1; k < dist; ++k) if (theirs >> ((r + dr * k) * 8 + c + dc * k) & 1) return;
-	out[n].from = (uint8_t)(r * 8 + c); out[n].to = (uint8_t)(tr * 8 + tc); ++n;
+	const int d = __builtin_popcountll((mine | theirs) & L) * step;
+	const int tu = pos + d, td = pos - d;
+	const bool up = tu < 64 && ((L & ~mine) >> tu & 1) && (theirs & L & ((1ull << tu) - (2ull << pos))) == 0;
+	const bool dn = td >= 0 && ((L & ~mine) >> td & 1) && (theirs & L & ((1ull << pos) - (2ull << td))) == 0;
+	if (up_first) { if (up) { out[n].from = (uint8_t)pos; out[n].to = (uint8_t)tu; ++n; } if (dn) { out[n].from = (uint8_t)pos; out[n].to = (uint8_t)td; ++n; } }
+	else { if (dn) { out[n].from = (uint8_t)pos; out[n].to = (uint8_t)td; ++n; } if (up) { out[n].from = (uint8_t)pos; out[n].to = (uint8_t)tu; ++n; } }
 }
 int generate(const GameState& s, Move* out)
 {
 	const bool wtm = (s.current_player & 1) == 0;
-	const uint64_t mine = wtm ? s.white : s.black, theirs = wtm ? s.black : s.white, all = mine | theirs;
+	const uint64_t mine = wtm ? s.white : s.black, theirs = wtm ? s.black : s.white;
 	int n = 0;
-	for (uint64_t rest = mine; rest; rest &= rest - 1) {
-		const int pos = __builtin_ctzll(rest), r = pos >> 3, c = pos & 7;
-		int d = line_count(all, r, c, 0, 1);
-		try_move(mine, theirs, r, c, 0, -1, d, out, n); try_move(mine, theirs, r, c, 0, +1, d, out, n);
-		d = line_count(all, r, c, 1, 0);
-		try_move(mine, theirs, r, c, +1, 0, d, out, n); try_move(mine, theirs, r, c, -1, 0, d, out, n);
-		d = line_count(all, r, c, 1, 1);
-		try_move(mine, theirs, r, c, -1, -1, d, out, n); try_move(mine, theirs, r, c, +1, +1, d, out, n);
-		d = line_count(all, r, c, 1, -1);
-		try_move(mine, theirs, r, c, -1, +1, d, out, n); try_move(mine, theirs, r, c, +1, -1, d, out, n);
+	for (uint64_t rest = mine; rest; rest &= rest - 1) {                   // ascending squares; W E | N S | SW NE | SE NW (:194-223)
+		const int pos = __builtin_ctzll(rest);
+		line_moves(mine, theirs, g_lines.m[0][pos], 1, pos, false, out, n);
+		line_moves(mine, theirs, g_lines.m[1][pos], 8, pos, true, out, n);
+		line_moves(mine, theirs, g_lines.m[2][pos], 9, pos, false, out, n);
+		line_moves(mine, theirs, g_lines.m[3][pos], 7, pos, false, out, n);
 	}
 	return n;
 }
