@@ -65,6 +65,48 @@ def test_gpu_player_refuses_to_play_without_a_gpu():
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
+# ---- host logic of the GPU MCTS player with the GPU library replaced by a TEST stub (LD_PRELOAD, tests/helpers/fake_gpu.cpp) ----
+@pytest.fixture(scope="module")
+def fake_gpu():
+    so = os.path.join(ROOT, "tests", "helpers", "libfake_gpu.so")
+    src = os.path.join(ROOT, "tests", "helpers", "fake_gpu.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, src])
+    return so
+
+
+def run_with_fake_gpu(fake_gpu, *args):
+    env = dict(os.environ, LD_PRELOAD=fake_gpu)
+    r = subprocess.run([LAUNCHER, "--xml", XML] + list(args), capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_mcts_host_logic_is_deterministic_and_reuses_its_tree(fake_gpu):
+    """Selection with virtual loss, lazy expansion, two pipelined batches, transposition table, tree reuse and GC, final-move
+    rule -- everything above the C ABI, with fixed seeds and a simulation budget: two runs must agree move for move."""
+    args = ("--p1", "mcts move_sim_limit=400000 gpu_batch=512 playouts_per_leaf=8 random_seed=3 philox_seed=4", "--p2", "random random_seed=5",
+            "--ng", "1", "--rl", "40", "--seed", "6")
+    a = run_with_fake_gpu(fake_gpu, *args); b = run_with_fake_gpu(fake_gpu, *args)
+    assert a["rounds"] == b["rounds"] and a["first_move"] == b["first_move"]
+    sa, sb = a["players"][0]["stats"], b["players"][0]["stats"]
+    assert sa["last_root_stats"] == sb["last_root_stats"] and sa["runs_per_move"] == sb["runs_per_move"]
+    assert float(sa["gpu_batches"]) > 100 and float(sa["reused_root_visits"]) > 0          # the next root was found in the old tree
+    assert float(sa["tree_gc_runs"]) >= 1 and float(sa["tree_gc_freed_nodes"]) > 0         # 50 k selections per move: the tree outgrows the GC threshold
+    # the merged root statistics are consistent: visits are whole batches of playouts, values never exceed visits
+    for item in sa["last_root_stats"].split(","):
+        v, w, bl = item.split(":")
+        assert int(v) % 8 == 0 and float(w) + float(bl) <= int(v) + 1e-3
+
+
+def test_root_parallel_trees_in_one_process(fake_gpu):
+    res = run_with_fake_gpu(fake_gpu, "--p1", "mcts move_sim_limit=60000 devices=0,0,0 random_seed=3 philox_seed=4", "--p2", "random random_seed=5",
+                            "--ng", "1", "--rl", "10", "--seed", "6")
+    st = res["players"][0]["stats"]
+    total = sum(int(x.split(":")[0]) for x in st["last_root_stats"].split(","))
+    assert total >= 3 * (60000 // 3 // 32) * 32 * 0.9                                    # three trees' visits were merged at the root
+
+
 # ---- Pan host rules plugin (createGameRules for GraWPanaZasadyV2) -----------------------------------------------
 def test_pan_host_rules_plugin_vs_oracle():
     from oracle import pan
