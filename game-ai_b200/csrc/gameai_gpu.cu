@@ -52,7 +52,7 @@ struct gai_ctx {
 	Buf d_in, d_in2, d_out, d_out2, d_out3, d_boards, d_stm, d_misc, d_prep;
 	Buf h_in, h_in2, h_out, h_out2, h_out3;
 	// async rollout bookkeeping
-	gai_loa_result* pending_out = nullptr; uint32_t pending_n = 0;
+	gai_loa_result* pending_out = nullptr; uint32_t pending_n = 0; bool pending_direct = false;   // direct: results were DMA-ed into the caller's pinned buffer
 	// nccl
 	NcclApi nccl; ncclComm_t comm = nullptr; int rank = 0, world = 1;
 };
@@ -227,8 +227,8 @@ int gai_sync(gai_ctx* ctx)
 	if (!ctx) return GAI_ERR_INVALID;
 	CU(cudaStreamSynchronize(ctx->stream));
 	if (ctx->pending_out) {
-		memcpy(ctx->pending_out, ctx->h_out.p, (size_t)ctx->pending_n * sizeof(gai_loa_result));
-		ctx->pending_out = nullptr; ctx->pending_n = 0;
+		if (!ctx->pending_direct) memcpy(ctx->pending_out, ctx->h_out.p, (size_t)ctx->pending_n * sizeof(gai_loa_result));
+		ctx->pending_out = nullptr; ctx->pending_n = 0; ctx->pending_direct = false;
 	}
 	return GAI_OK;
 }
@@ -364,7 +364,7 @@ int gai_loa_pack_states(const gai_loa_state* states, uint32_t n, void* boards16,
 }
 
 static int rollout_host_enqueue(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
-                                uint64_t key, uint64_t first_id)
+                                uint64_t key, uint64_t first_id, gai_loa_result* out, bool* direct)
 {
 	if (!leaves) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: leaves is NULL");
 	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: playouts_per_leaf must be >= 1");
@@ -372,7 +372,11 @@ static int rollout_host_enqueue(gai_ctx* ctx, const gai_loa_state* leaves, uint3
 	CU(cudaSetDevice(ctx->device));
 	const size_t sb = (size_t)n_leaves * sizeof(gai_loa_state);
 	const size_t bb = (size_t)n_leaves * 16, wb = (size_t)((n_leaves + 31u) / 32u) * 4, rb = (size_t)n_leaves * sizeof(gai_loa_result);
-	EN(ctx->h_out, rb, true);
+	// results: DMA straight into the caller's buffer when it is pinned, else into pinned staging (copied out by gai_sync)
+	cudaPointerAttributes po;
+	*direct = cudaPointerGetAttributes(&po, out) == cudaSuccess && po.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!*direct) EN(ctx->h_out, rb, true);
 	EN(ctx->d_in, sb, false); EN(ctx->d_boards, bb, false); EN(ctx->d_stm, wb, false); EN(ctx->d_out, rb, false);
 	// The reference's 24-byte GameState records go to the device as they are and are split into 16-byte boards + side
 	// bits THERE (k_split_states): no host-side repack pass.  Pinned caller memory is DMA-ed directly; pageable memory
@@ -387,7 +391,7 @@ static int rollout_host_enqueue(gai_ctx* ctx, const gai_loa_state* leaves, uint3
 	LAUNCHED("k_split_states");
 	int r = enqueue_rollout(ctx, ctx->d_boards.p, (const uint32_t*)ctx->d_stm.p, n_leaves, ppl, max_plies, key, first_id, ctx->d_out.p);
 	if (r) return r;
-	CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(*direct ? (void*)out : ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
 	return GAI_OK;
 }
@@ -398,9 +402,10 @@ int gai_loa_rollout_async(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_
 	if (!ctx) return GAI_ERR_INVALID;
 	if (n_leaves == 0) return GAI_OK;
 	if (!out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_async: out is NULL");
-	int r = rollout_host_enqueue(ctx, leaves, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id);
+	bool direct = false;
+	int r = rollout_host_enqueue(ctx, leaves, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id, out, &direct);
 	if (r) return r;
-	ctx->pending_out = out; ctx->pending_n = n_leaves;
+	ctx->pending_out = out; ctx->pending_n = n_leaves; ctx->pending_direct = direct;
 	return GAI_OK;
 }
 
