@@ -231,8 +231,8 @@ GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, const SweepTabs& lu
 	// covers four rows of one half; the field-count table turns it into four byte lanes (popcount of the two sense bits),
 	// weighted by the plane and accumulated -- IDP.4A + LDS + IMAD per byte, nothing on the ALU pipe.
 	const u32 BM = 0x01010101u;
-	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p1), c_one, 1, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p1), c_one, 1, tlo);
-	thi = GAI_MADC(tpc_of<1>(lut.tpc, p1), c_one, 1, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p1), c_one, 1, thi);
+	tlo = tlo + tpc_of<0>(lut.tpc, p1) + tpc_of<2>(lut.tpc, p1);          // weight 1: one three-input add each (the kernel is issue bound)
+	thi = thi + tpc_of<1>(lut.tpc, p1) + tpc_of<3>(lut.tpc, p1);
 	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p2), c_two, 2, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p2), c_two, 2, tlo);
 	thi = GAI_MADC(tpc_of<1>(lut.tpc, p2), c_two, 2, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p2), c_two, 2, thi);
 	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p4), c_four, 4, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p4), c_four, 4, tlo);
@@ -293,10 +293,8 @@ GAI_HDI void sweep_select(const RowCounts& rc, u32 idx, const SweepTabs& t, int*
 	const u32 x1 = rotl16(y1, (int)sh);
 	// moves per column, one byte lane each (<= 8), inclusive prefix sums
 	const u32 A = pack16(xr, xc), B = pack16(x1, x2);
-	u32 cl = tpc_of<0>(t.tpc, A), ch = tpc_of<1>(t.tpc, A);
-	cl = GAI_MADC(tpc_of<2>(t.tpc, A), c_one, 1, cl); ch = GAI_MADC(tpc_of<3>(t.tpc, A), c_one, 1, ch);
-	cl = GAI_MADC(tpc_of<0>(t.tpc, B), c_one, 1, cl); ch = GAI_MADC(tpc_of<1>(t.tpc, B), c_one, 1, ch);
-	cl = GAI_MADC(tpc_of<2>(t.tpc, B), c_one, 1, cl); ch = GAI_MADC(tpc_of<3>(t.tpc, B), c_one, 1, ch);
+	const u32 cl = (tpc_of<0>(t.tpc, A) + tpc_of<2>(t.tpc, A)) + (tpc_of<0>(t.tpc, B) + tpc_of<2>(t.tpc, B));     // three-input adds
+	const u32 ch = (tpc_of<1>(t.tpc, A) + tpc_of<3>(t.tpc, A)) + (tpc_of<1>(t.tpc, B) + tpc_of<3>(t.tpc, B));
 	const u32 pl = cl * 0x01010101u, ph = ch * 0x01010101u + (pl >> 24) * 0x01010101u;
 	const u32 yk = (k + 1u) * 0x01010101u;
 	const u32 hlo = ((pl | 0x80808080u) - yk) & 0x80808080u, hhi = ((ph | 0x80808080u) - yk) & 0x80808080u;
