@@ -289,7 +289,10 @@ def main():
         if prof:
             ach = plies_per_s / world * prof["warp_inst_per_thread_ply"]       # per GPU
             roof.update({"achieved": ach / 1e9, "frac": ach / peak_issue, "warp_inst_per_thread_ply": prof["warp_inst_per_thread_ply"],
-                         "thread_inst_per_ply": prof.get("thread_inst_per_ply"), "traffic": prof.get("dram_bytes_per_launch"),
+                         "thread_inst_per_ply": prof.get("thread_inst_per_ply"),
+                         # ncu dram bytes of the captured launch (262144 leaves), scaled to this launch's leaf count
+                         "traffic": prof.get("dram_bytes_per_launch") * n / prof["leaves_per_launch"] if prof.get("dram_bytes_per_launch") and prof.get("leaves_per_launch") else prof.get("dram_bytes_per_launch"),
+                         "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture (%s leaves per launch), scaled by leaves" % prof.get("leaves_per_launch"),
                          "source": prof.get("source")})
         alg_bytes = n * (16 + 16) + ((n + 31) // 32) * 4                  # boards in, results out (per launch)
         peaks = {}

@@ -18,6 +18,7 @@ d = {
     "source": "profiles/r01_v15_ncu_summary.txt <- %s (ncu --set full --clock-control none, one launch of %s; %d leaves x %d playouts)" % (
         os.path.basename(rep), vals[hdr.index("Kernel Name")].split("(")[0], b["config"]["leaves_per_gpu"], b["config"]["playouts_per_leaf"]),
     "tag": tag,
+    "leaves_per_launch": b["config"]["leaves_per_gpu"],
     "thread_plies_per_launch": plies_per_launch,
     "warp_inst_executed": wi,
     "warp_inst_per_thread_ply": wi / plies_per_launch,
