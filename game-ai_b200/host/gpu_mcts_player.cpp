@@ -47,6 +47,38 @@ struct Node {
 struct Key { uint64_t w, b, cp; bool operator==(const Key& o) const { return w == o.w && b == o.b && cp == o.cp; } };
 struct KeyHash { size_t operator()(const Key& k) const { uint64_t h = k.w * 0x9E3779B97F4A7C15ull ^ (k.b + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^ k.cp; h ^= h >> 29; return (size_t)h; } };
 
+// Transposition table (makeTreeNode, MCTSPlayer.cpp:634-662, keyed there by the ToString text): open addressing, one
+// 32-byte entry per position, no allocation per insert (std::unordered_map cost two cache misses and a malloc per node).
+struct FlatTable {
+	struct Entry { Key k; int32_t idx; uint32_t used; };
+	std::vector<Entry> slots; size_t mask = 0, count = 0;
+	void init(size_t cap) { size_t c = 1; while (c < cap) c <<= 1; slots.assign(c, Entry{ Key{ 0, 0, 0 }, -1, 0 }); mask = c - 1; count = 0; }
+	void clear() { if (!slots.empty()) init(slots.size()); }
+	int find(const Key& k) const
+	{
+		if (slots.empty()) return -1;
+		for (size_t i = KeyHash()(k) & mask;; i = (i + 1) & mask) {
+			const Entry& e = slots[i];
+			if (!e.used) return -1;
+			if (e.k == k) return e.idx;
+		}
+	}
+	void emplace(const Key& k, int idx)
+	{
+		if (slots.empty()) init(1u << 19);
+		if (2 * (count + 1) > slots.size()) {                                // keep the load factor under 1/2
+			std::vector<Entry> old; old.swap(slots);
+			init(old.size() * 2);
+			for (const Entry& e : old) if (e.used) emplace(e.k, e.idx);
+		}
+		for (size_t i = KeyHash()(k) & mask;; i = (i + 1) & mask) {
+			Entry& e = slots[i];
+			if (!e.used) { e.k = k; e.idx = idx; e.used = 1; ++count; return; }
+			if (e.k == k) { e.idx = idx; return; }
+		}
+	}
+};
+
 struct Settings {
 	int player = 0, num_players = 2;
 	float C = 1.0f, eps = 0.005f;
@@ -65,7 +97,7 @@ struct Tree {
 	Settings cfg;
 	std::vector<Node> nodes;
 	std::vector<Edge> edges;
-	std::unordered_map<Key, int, KeyHash> table;
+	FlatTable table;
 	std::mt19937 rng;
 	uint32_t visit_id = 0;
 	uint64_t next_playout_id = 0, key = 0;
@@ -82,9 +114,9 @@ struct Tree {
 	int make_node(GameState* s)                               // takes ownership of s
 	{
 		const Key k = key_of(s);
-		auto it = table.find(k);
-		if (it != table.end()) { rules->ReleaseGameState(s); return it->second; }
-		if (nodes.capacity() == 0) { nodes.reserve(1u << 18); edges.reserve(1u << 21); table.reserve(1u << 19); }      // no rehash / regrowth mid-search
+		const int known = table.find(k);
+		if (known >= 0) { rules->ReleaseGameState(s); return known; }
+		if (nodes.capacity() == 0) { nodes.reserve(1u << 18); edges.reserve(1u << 21); }      // no regrowth mid-search
 		Node n; n.state = s; n.cp = (uint8_t)rules->GetCurrentPlayer(s);
 		n.terminal = rules->IsTerminal(s);
 		if (n.terminal) { rules->Score(s, n.score); n.n_edges = 0; }
@@ -144,27 +176,27 @@ struct Tree {
 	// edge per level -- 5 of the 7 microseconds a selection took on a 200 k-node tree.
 	int choose_edge(const Node& n)
 	{
-		const double lnN = std::log((double)n.visits + 1.0);
+		const float lnN = (float)std::log((double)n.visits + 1.0);
 		const int ne = n.n_edges < 128 ? n.n_edges : 128;                 // <= 96 moves (LinesOfActionZasady.cpp:226)
-		double val[128];
+		float val[128];
 		const Edge* ed = edges.data() + n.first_edge;
 		const int cp = n.cp;
-		for (int i = 0; i < ne; ++i) {                                    // no branches: the compiler vectorises sqrt and divide
-			const double oo = 1.0 / (1.0 + (double)ed[i].visits);
-			val[i] = (double)ed[i].value[cp] * oo + (double)cfg.C * std::sqrt(lnN * oo);
+		for (int i = 0; i < ne; ++i) {                                    // no branches: the compiler vectorises sqrt and divide (8 lanes)
+			const float oo = 1.0f / (1.0f + (float)ed[i].visits);
+			val[i] = ed[i].value[cp] * oo + cfg.C * std::sqrt(lnN * oo);
 		}
 		for (;;) {
-			double best = -1e300; int ties[128]; int nt = 0;
+			float best = -1e30f; int ties[128]; int nt = 0;
 			for (int i = 0; i < ne; ++i) {
-				const double v = val[i];
+				const float v = val[i];
 				if (v > best) { best = v; nt = 0; ties[nt++] = i; }
 				else if (v == best) ties[nt++] = i;
 			}
-			if (nt == 0 || best == -1e300) return -1;
+			if (nt == 0 || best == -1e30f) return -1;
 			const int pick = ties[nt == 1 ? 0 : std::uniform_int_distribution<int>(0, nt - 1)(rng)];
 			const int child = ed[pick].child;
 			if (child < 0 || nodes[child].visit_id != visit_id) return pick;
-			val[pick] = -1e300;                                           // would close a loop: choose again without it
+			val[pick] = -1e30f;                                           // would close a loop: choose again without it
 		}
 	}
 
