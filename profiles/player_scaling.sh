@@ -18,4 +18,4 @@ print(json.dumps({'world': $W, 'rank': $r, 'rounds': d['rounds'], 'playouts_per_
   done
 }
 run 1
-[ "$N" -gt 1 ] && run $N
+if [ "$N" -gt 1 ]; then run $N; fi
