@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """Pan determinized-rollout throughput on one B200 (config 5 of BASELINE.json), with the reference rules timed beside it.
+MEASUREMENT SCRIPT, not product: oracle/ serves as corpus generator, as the checker of the first 2048 deals and as the
+CPU baseline beside the GPU number (like bench.py's cpu_baseline leg).
 usage (GPU box): python profiles/pan_bench.py > gpurun_out/pan_bench.json"""
 import json, os, sys, time
 import numpy as np

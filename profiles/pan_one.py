@@ -1,3 +1,5 @@
+"""MEASUREMENT SCRIPT, not product: one Pan rollout launch (3 players) for ncu; oracle/ only generates the corpus of deals.
+usage (GPU box): python profiles/pan_one.py [max_plies]"""
 import sys, os
 sys.path.insert(0, '/root/repo')
 import numpy as np, gameai_b200 as g

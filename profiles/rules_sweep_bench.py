@@ -3,6 +3,8 @@
 synthetic positions through the C ABI with HOST buffers (H2D + kernel + D2H inside the timed call), for the three device
 formulations of the rules, with the reference rules on one host core beside it.  The parity of the same sweep is a test
 (tests/test_gpu_rules.py::test_full_size_sweep_1m_positions); this script only times it.
+MEASUREMENT SCRIPT, not product: oracle/ serves as corpus generator and as the one-core CPU baseline (like bench.py's
+cpu_baseline leg).
 usage (GPU box): python profiles/rules_sweep_bench.py > gpurun_out/rules_sweep.json"""
 import json, os, sys, time
 import numpy as np

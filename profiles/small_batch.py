@@ -5,10 +5,9 @@ import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gameai_b200 as g
-from oracle import loa
 
 eng = g.GpuRollout(0)
-S = loa.port().gen_reachable(16384, 0x5EED)
+S = eng.gen_reachable(16384, 0x5EED)            # the device corpus generator (k_gen_reachable); nothing from oracle/ here
 out = []
 for n, ppl in ((256, 32), (1024, 32), (1024, 128), (4096, 32), (16384, 32)):
     eng.rollout(S[:n], ppl, 50000, 1, 0)
