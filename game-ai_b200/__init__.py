@@ -72,6 +72,10 @@ def lib():
         L.gai_loa_rollout.argtypes = [_vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp, _vp]
         L.gai_loa_rollout_async.argtypes = [_vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp]
         L.gai_last_rollout_stats.argtypes = [_vp, _vp]
+        L.gai_loa_rollout_submit.argtypes = [_vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp, ctypes.POINTER(_i32)]
+        L.gai_loa_rollout_children_submit.argtypes = [_vp, _vp, _u32, _vp, _u32, _u32, _u64, _u64, _vp, ctypes.POINTER(_i32)]
+        L.gai_wait.argtypes = [_vp, _i32, _vp]
+        L.gai_inflight.argtypes = [_vp]
         L.gai_loa_rollout_device.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _vp, _vp]
         L.gai_loa_playout_trace.argtypes = [_vp, _vp, _u32, _u32, _u64, _u64, _vp, _vp, _vp]
         L.gai_loa_gen_reachable.argtypes = [_vp, _u32, _u64, _u32, _vp, _vp, _vp]
@@ -228,6 +232,31 @@ class GpuRollout:
     def rollout_async(self, states, out, playouts_per_leaf, max_plies, key, first_id):
         """Enqueue and return; `out` (n,4) uint32 is valid after sync().  One batch in flight per context."""
         self._ck(self.L.gai_loa_rollout_async(self.h, states.ctypes.data, states.shape[0], playouts_per_leaf, max_plies, key, first_id, out.ctypes.data))
+
+    # ticketed batches: up to GAI_MAX_INFLIGHT queued per context
+    def submit(self, states, out, playouts_per_leaf, max_plies, key, first_id):
+        """Queue a leaf batch; `states` (n,3) uint64 and `out` (n,4) uint32 must stay alive until wait(ticket)."""
+        t = _i32(-1)
+        self._ck(self.L.gai_loa_rollout_submit(self.h, states.ctypes.data, states.shape[0], playouts_per_leaf, max_plies, key, first_id,
+                                               out.ctypes.data, ctypes.byref(t)))
+        return t.value
+
+    def submit_children(self, parents, child_offsets, out, playouts_per_leaf, max_plies, key, first_id):
+        """Queue a batch-by-expansion: every successor of every parent is a leaf (out: (child_offsets[-1], 4) uint32)."""
+        t = _i32(-1)
+        off = np.ascontiguousarray(child_offsets, dtype=np.uint32)
+        assert off.shape[0] == parents.shape[0] + 1
+        self._ck(self.L.gai_loa_rollout_children_submit(self.h, parents.ctypes.data, parents.shape[0], off.ctypes.data, playouts_per_leaf, max_plies,
+                                                        key, first_id, out.ctypes.data, ctypes.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        st = RolloutStats()
+        self._ck(self.L.gai_wait(self.h, ticket, ctypes.byref(st)))
+        return _stats(st)
+
+    def inflight(self):
+        return int(self.L.gai_inflight(self.h))
 
     def last_rollout_stats(self):
         st = RolloutStats()

@@ -35,8 +35,19 @@ struct Id128 { char b[128]; };
 
 } // namespace
 
+// one queued batch of the ticketed API: own staging + device buffers, so that batch k+1 can be uploaded and queued
+// while batch k plays out
+struct Slot {
+	Buf d_in, d_off, d_boards, d_side, d_stm, d_out, d_prep, d_misc;
+	Buf h_in, h_off, h_out, h_stat;
+	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	bool busy = false, direct = false, children = false;
+	gai_loa_result* out = nullptr; uint32_t n_out = 0; unsigned gen = 0;
+};
+
 struct gai_ctx {
 	int device = 0;
+	Slot slots[GAI_MAX_INFLIGHT];
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	cudaDeviceProp prop;
@@ -56,6 +67,8 @@ struct gai_ctx {
 	// nccl
 	NcclApi nccl; ncclComm_t comm = nullptr; int rank = 0, world = 1;
 };
+
+extern "C" int gai_sync(gai_ctx* ctx);
 
 namespace {
 
@@ -100,35 +113,51 @@ int rollout_grid(const gai_ctx* ctx, uint64_t total_items)
 }
 
 // enqueue: zero out/stat/counter, rollout kernel.  d_misc layout: [0..1] stats u64, [2] work counter.
-int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl,
+int enqueue_rollout(gai_ctx* ctx, Buf& misc, Buf& prep, cudaEvent_t ev_k0, cudaEvent_t ev_k1, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl,
                     uint32_t max_plies, uint64_t key, uint64_t first_id, void* d_out)
 {
-	EN(ctx->d_misc, 64, false);
+	EN(misc, 128, false);
 	// d_prep: [n x 64 B rotations][n x u32 order][n x u8 piece counts][64 x u32 histogram + cursors]
 	const size_t prep_b = (size_t)n_leaves * 64, ord_b = (size_t)n_leaves * 4, pc_b = ((size_t)n_leaves + 255) / 256 * 256;
-	if (ctx->impl >= 1) EN(ctx->d_prep, prep_b + ord_b + pc_b + 256, false);
-	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
+	if (ctx->impl >= 1) EN(prep, prep_b + ord_b + pc_b + 256, false);
+	CU(cudaMemsetAsync(misc.p, 0, 64, ctx->stream));
 	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
-	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	CU(cudaEventRecord(ev_k0, ctx->stream));
 	if (ctx->impl >= 1) {
 		// rotations of every leaf, once per batch (inside the timed region: it is part of the step)
-		char* pb = (char*)ctx->d_prep.p;
+		char* pb = (char*)prep.p;
 		uint32_t* d_order = (uint32_t*)(pb + prep_b); uint8_t* d_pc = (uint8_t*)(pb + prep_b + ord_b); uint32_t* d_hist = (uint32_t*)(pb + prep_b + ord_b + pc_b);
 		CU(cudaMemsetAsync(d_hist, 0, 256, ctx->stream));
 		launch_loa_prepare_leaves(d_boards, n_leaves, pb, d_pc, d_hist, d_order, ctx->stream);
 		LAUNCHED("k_prepare_leaves"); ctx->launches += 1;      // + k_order_leaves
 		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
-		                        (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
+		                        (uint64_t*)misc.p, (unsigned long long*)misc.p + 2,
 		                        ctx->impl == 2 ? ctx->sweep_threads : ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2 ? ctx->sweep_unroll : 0, ctx->stream);
 	} else
 		launch_loa_rollout(d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
-		                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2,
+		                   (uint64_t*)misc.p, (unsigned long long*)misc.p + 2,
 		                   ctx->threads, rollout_grid(ctx, total), ctx->stream);
 	LAUNCHED("k_rollout");
-	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+	CU(cudaEventRecord(ev_k1, ctx->stream));
 	return GAI_OK;
 }
+int enqueue_rollout(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves, uint32_t ppl,
+                    uint32_t max_plies, uint64_t key, uint64_t first_id, void* d_out)
+{
+	return enqueue_rollout(ctx, ctx->d_misc, ctx->d_prep, ctx->ev[1], ctx->ev[2], d_boards, d_stm, n_leaves, ppl, max_plies, key, first_id, d_out);
+}
+
+int tickets_out(const gai_ctx* ctx) { int k = 0; for (const Slot& sl : ctx->slots) k += sl.busy ? 1 : 0; return k; }
+// The synchronous entry points share the context's scratch buffers with each other and with gai_loa_rollout_async:
+// finish a pending async batch first, refuse to run while ticketed batches are queued.
+int quiesce(gai_ctx* ctx, const char* who)
+{
+	if (tickets_out(ctx)) return fail(ctx, GAI_ERR_INVALID, "%s: ticketed batches are outstanding on this context (gai_wait them first)", who);
+	if (ctx->pending_out) return gai_sync(ctx);
+	return GAI_OK;
+}
+#define QUIESCE(who) do { int q_ = quiesce(ctx, who); if (q_) return q_; } while (0)
 
 int fill_stats(gai_ctx* ctx, gai_rollout_stats* stats, bool have_total)
 {
@@ -178,6 +207,7 @@ int gai_create(int device, gai_ctx** out)
 		fail(nullptr, GAI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return GAI_ERR_CUDA;
 	}
 	for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+	for (Slot& sl : ctx->slots) for (auto& ev : sl.ev) cudaEventCreate(&ev);
 	{	// line LUT of the fast rules: built on the host from its definition, resident in HBM/L2, staged to shared memory per CTA
 		const int lb = loa_fast_lut_bytes();
 		uint16_t* h = (uint16_t*)malloc(lb);
@@ -201,6 +231,10 @@ void gai_destroy(gai_ctx* ctx)
 	for (Buf* b : { &ctx->d_in, &ctx->d_in2, &ctx->d_out, &ctx->d_out2, &ctx->d_out3, &ctx->d_boards, &ctx->d_stm, &ctx->d_misc, &ctx->d_prep,
 	                &ctx->h_in, &ctx->h_in2, &ctx->h_out, &ctx->h_out2, &ctx->h_out3 }) release(*b);
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+	for (Slot& sl : ctx->slots) {
+		for (Buf* b : { &sl.d_in, &sl.d_off, &sl.d_boards, &sl.d_side, &sl.d_stm, &sl.d_out, &sl.d_prep, &sl.d_misc, &sl.h_in, &sl.h_off, &sl.h_out, &sl.h_stat }) release(*b);
+		for (auto& ev : sl.ev) if (ev) cudaEventDestroy(ev);
+	}
 	if (ctx->d_lut) cudaFree(ctx->d_lut);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -274,6 +308,7 @@ int gai_loa_movegen(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint8
 	if (n == 0) return GAI_OK;
 	if (!states || !counts || !moves) return fail(ctx, GAI_ERR_INVALID, "gai_loa_movegen: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_movegen");
 	const size_t sb = (size_t)n * sizeof(gai_loa_state), mb = (size_t)n * GAI_LOA_MAX_MOVES * sizeof(gai_loa_move);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, mb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -294,6 +329,7 @@ int gai_loa_apply(gai_ctx* ctx, const gai_loa_state* states, const gai_loa_move*
 	if (n == 0) return GAI_OK;
 	if (!states || !mv || !out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_apply: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_apply");
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_in2, (size_t)n * 2, false); EN(ctx->d_out, sb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -311,6 +347,7 @@ int gai_loa_terminal(gai_ctx* ctx, const gai_loa_state* states, uint32_t n, uint
 	if (n == 0) return GAI_OK;
 	if (!states || !terminal || !score) return fail(ctx, GAI_ERR_INVALID, "gai_loa_terminal: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_terminal");
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 2, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -328,6 +365,7 @@ int gai_loa_successor_hash(gai_ctx* ctx, const gai_loa_state* states, uint32_t n
 	if (n == 0) return GAI_OK;
 	if (!states || !hash) return fail(ctx, GAI_ERR_INVALID, "gai_loa_successor_hash: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_successor_hash");
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, (size_t)n * 8, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -369,6 +407,7 @@ static int rollout_host_enqueue(gai_ctx* ctx, const gai_loa_state* leaves, uint3
 	if (!leaves) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: leaves is NULL");
 	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: playouts_per_leaf must be >= 1");
 	if (ctx->pending_out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: a batch is already in flight on this context (call gai_sync)");
+	if (tickets_out(ctx)) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout: ticketed batches are outstanding on this context (gai_wait them first)");
 	CU(cudaSetDevice(ctx->device));
 	const size_t sb = (size_t)n_leaves * sizeof(gai_loa_state);
 	const size_t bb = (size_t)n_leaves * 16, wb = (size_t)((n_leaves + 31u) / 32u) * 4, rb = (size_t)n_leaves * sizeof(gai_loa_result);
@@ -433,6 +472,109 @@ int gai_loa_rollout(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves
 	return fill_stats(ctx, stats, true);
 }
 
+// ---- ticketed batches ------------------------------------------------------------------------------
+static int submit_batch(gai_ctx* ctx, const gai_loa_state* states, uint32_t n_states, const uint32_t* offsets, uint32_t ppl, uint32_t max_plies,
+                        uint64_t key, uint64_t first_id, gai_loa_result* out, int* ticket, const char* who)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (!ticket) return fail(ctx, GAI_ERR_INVALID, "%s: ticket is NULL", who);
+	*ticket = -1;
+	if (n_states && (!states || !out)) return fail(ctx, GAI_ERR_INVALID, "%s: NULL buffer", who);
+	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "%s: playouts_per_leaf must be >= 1", who);
+	if (ctx->pending_out) return fail(ctx, GAI_ERR_INVALID, "%s: a gai_loa_rollout_async batch is in flight on this context (call gai_sync)", who);
+	int si = -1;
+	for (int i = 0; i < GAI_MAX_INFLIGHT; ++i) if (!ctx->slots[i].busy) { si = i; break; }
+	if (si < 0) return fail(ctx, GAI_ERR_INVALID, "%s: all batch slots of this context are busy (gai_wait one first)", who);
+	Slot& sl = ctx->slots[si];
+	CU(cudaSetDevice(ctx->device));
+	uint32_t n_leaves = n_states;
+	if (offsets && n_states) {
+		if (offsets[0] != 0) return fail(ctx, GAI_ERR_INVALID, "%s: child_offsets[0] must be 0", who);
+		for (uint32_t i = 0; i < n_states; ++i)
+			if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > GAI_LOA_MAX_MOVES) return fail(ctx, GAI_ERR_INVALID, "%s: child_offsets must be non-decreasing with at most 96 children per parent", who);
+		n_leaves = offsets[n_states];
+	}
+	sl.children = offsets != nullptr; sl.out = out; sl.n_out = n_leaves; sl.direct = false;
+	EN(sl.h_stat, 64, true); EN(sl.d_misc, 128, false);
+	memset(sl.h_stat.p, 0, 64);
+	CU(cudaEventRecord(sl.ev[0], ctx->stream));
+	if (n_leaves == 0) {                       // nothing to play: the ticket completes immediately
+		CU(cudaEventRecord(sl.ev[1], ctx->stream)); CU(cudaEventRecord(sl.ev[2], ctx->stream)); CU(cudaEventRecord(sl.ev[3], ctx->stream));
+		sl.busy = true; sl.gen += 1; *ticket = (int)(sl.gen * GAI_MAX_INFLIGHT + (unsigned)si);
+		return GAI_OK;
+	}
+	const size_t sb = (size_t)n_states * sizeof(gai_loa_state), ob = offsets ? (size_t)(n_states + 1) * 4 : 0;
+	const size_t bb = (size_t)n_leaves * 16, wb = (size_t)((n_leaves + 31u) / 32u) * 4, rb = (size_t)n_leaves * sizeof(gai_loa_result);
+	cudaPointerAttributes po;
+	sl.direct = cudaPointerGetAttributes(&po, out) == cudaSuccess && po.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!sl.direct) EN(sl.h_out, rb, true);
+	EN(sl.d_in, sb, false); EN(sl.d_boards, bb, false); EN(sl.d_stm, wb, false); EN(sl.d_out, rb, false);
+	cudaPointerAttributes pa; const void* src = states;
+	const bool pinned = cudaPointerGetAttributes(&pa, states) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!pinned) { EN(sl.h_in, sb, true); memcpy(sl.h_in.p, states, sb); src = sl.h_in.p; }
+	CU(cudaMemcpyAsync(sl.d_in.p, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+	uint32_t* d_bad = (uint32_t*)((char*)sl.d_misc.p + 64);
+	CU(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+	if (offsets) {
+		EN(sl.h_off, ob, true); EN(sl.d_off, ob, false); EN(sl.d_side, n_leaves, false);
+		memcpy(sl.h_off.p, offsets, ob);
+		CU(cudaMemcpyAsync(sl.d_off.p, sl.h_off.p, ob, cudaMemcpyHostToDevice, ctx->stream));
+		launch_loa_expand_children(sl.d_in.p, n_states, (const uint32_t*)sl.d_off.p, sl.d_boards.p, (uint8_t*)sl.d_side.p, d_bad, ctx->stream);
+		LAUNCHED("k_expand_children");
+		launch_loa_pack_stm((const uint8_t*)sl.d_side.p, n_leaves, (uint32_t*)sl.d_stm.p, ctx->stream);
+		LAUNCHED("k_pack_stm");
+	} else {
+		launch_loa_split_states(sl.d_in.p, n_leaves, sl.d_boards.p, (uint32_t*)sl.d_stm.p, ctx->stream);
+		LAUNCHED("k_split_states");
+	}
+	int r = enqueue_rollout(ctx, sl.d_misc, sl.d_prep, sl.ev[1], sl.ev[2], sl.d_boards.p, (const uint32_t*)sl.d_stm.p, n_leaves, ppl, max_plies, key, first_id, sl.d_out.p);
+	if (r) return r;
+	CU(cudaMemcpyAsync(sl.direct ? (void*)out : sl.h_out.p, sl.d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(sl.h_stat.p, sl.d_misc.p, 16, cudaMemcpyDeviceToHost, ctx->stream));                   // {playouts, plies}
+	CU(cudaMemcpyAsync((char*)sl.h_stat.p + 16, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaEventRecord(sl.ev[3], ctx->stream));
+	sl.busy = true; sl.gen += 1; *ticket = (int)(sl.gen * GAI_MAX_INFLIGHT + (unsigned)si);
+	return GAI_OK;
+}
+
+int gai_loa_rollout_submit(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
+                           uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id, gai_loa_result* out, int* ticket)
+{
+	return submit_batch(ctx, leaves, n_leaves, nullptr, playouts_per_leaf, max_plies, philox_key, first_playout_id, out, ticket, "gai_loa_rollout_submit");
+}
+
+int gai_loa_rollout_children_submit(gai_ctx* ctx, const gai_loa_state* parents, uint32_t n_parents, const uint32_t* child_offsets,
+                                    uint32_t playouts_per_leaf, uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id,
+                                    gai_loa_result* out, int* ticket)
+{
+	if (ctx && !child_offsets) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_children_submit: child_offsets is NULL");
+	return submit_batch(ctx, parents, n_parents, child_offsets, playouts_per_leaf, max_plies, philox_key, first_playout_id, out, ticket, "gai_loa_rollout_children_submit");
+}
+
+int gai_inflight(const gai_ctx* ctx) { return ctx ? tickets_out(ctx) : 0; }
+
+int gai_wait(gai_ctx* ctx, int ticket, gai_rollout_stats* stats)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (stats) memset(stats, 0, sizeof *stats);
+	if (ticket < 0) return fail(ctx, GAI_ERR_INVALID, "gai_wait: bad ticket");
+	Slot& sl = ctx->slots[ticket % GAI_MAX_INFLIGHT];
+	if (!sl.busy || sl.gen != (unsigned)ticket / GAI_MAX_INFLIGHT) return fail(ctx, GAI_ERR_INVALID, "gai_wait: no such ticket outstanding");
+	sl.busy = false;                              // the slot is free again whatever happens below
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaEventSynchronize(sl.ev[3]));
+	const uint64_t* hs = (const uint64_t*)sl.h_stat.p;
+	if (sl.n_out && !sl.direct) memcpy(sl.out, sl.h_out.p, (size_t)sl.n_out * sizeof(gai_loa_result));
+	if (stats) {
+		stats->playouts = hs[0]; stats->plies = hs[1];
+		if (sl.n_out) { CU(cudaEventElapsedTime(&stats->kernel_ms, sl.ev[1], sl.ev[2])); CU(cudaEventElapsedTime(&stats->total_ms, sl.ev[0], sl.ev[3])); }
+	}
+	if (((const uint32_t*)sl.h_stat.p)[4]) return fail(ctx, GAI_ERR_INVALID, "gai_wait: a parent's move count on the device differs from child_offsets (caller and device rules disagree)");
+	return GAI_OK;
+}
+
 int gai_loa_rollout_device(gai_ctx* ctx, const void* d_boards, const uint32_t* d_stm, uint32_t n_leaves,
                            uint32_t playouts_per_leaf, uint32_t max_plies, uint64_t philox_key,
                            uint64_t first_playout_id, void* d_out, gai_rollout_stats* stats)
@@ -443,6 +585,7 @@ int gai_loa_rollout_device(gai_ctx* ctx, const void* d_boards, const uint32_t* d
 	if (!d_boards || !d_stm || !d_out) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_device: NULL buffer");
 	if (playouts_per_leaf == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_rollout_device: playouts_per_leaf must be >= 1");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_rollout_device");
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 	int r = enqueue_rollout(ctx, d_boards, d_stm, n_leaves, playouts_per_leaf, max_plies, philox_key, first_playout_id, d_out);
 	if (r) return r;
@@ -459,6 +602,7 @@ int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n,
 	if (n == 0) return GAI_OK;
 	if (!states || !outcome || !plies || !final_states) return fail(ctx, GAI_ERR_INVALID, "gai_loa_playout_trace: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_playout_trace");
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 4, false); EN(ctx->d_out3, sb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -484,6 +628,7 @@ int gai_loa_gen_reachable(gai_ctx* ctx, uint32_t n, uint64_t key, uint32_t max_k
 	if (max_k == 0) return fail(ctx, GAI_ERR_INVALID, "gai_loa_gen_reachable: max_k must be >= 1");
 	if ((d_boards == nullptr) != (d_stm == nullptr)) return fail(ctx, GAI_ERR_INVALID, "gai_loa_gen_reachable: d_boards and d_stm go together");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_loa_gen_reachable");
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in2, n, false);
 	if (host_states) EN(ctx->d_out3, sb, false);
@@ -515,6 +660,7 @@ int gai_pan_movegen(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int n
 	if (n == 0) return GAI_OK;
 	if (!states || !counts || !moves) return fail(ctx, GAI_ERR_INVALID, "gai_pan_movegen: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_pan_movegen");
 	const size_t sb = (size_t)n * 40, mb = (size_t)n * GAI_PAN_MAX_MOVES * 8;
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, mb, false); EN(ctx->d_misc, 64, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -537,6 +683,7 @@ int gai_pan_apply(gai_ctx* ctx, const gai_pan_state* states, const gai_pan_move*
 	if (n == 0) return GAI_OK;
 	if (!states || !mv || !out) return fail(ctx, GAI_ERR_INVALID, "gai_pan_apply: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_pan_apply");
 	const size_t sb = (size_t)n * 40;
 	EN(ctx->d_in, sb, false); EN(ctx->d_in2, (size_t)n * 8, false); EN(ctx->d_out, sb, false); EN(ctx->d_misc, 64, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -559,6 +706,7 @@ int gai_pan_terminal(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int 
 	if (n == 0) return GAI_OK;
 	if (!states || !terminal || !score || !ev0 || !ev1) return fail(ctx, GAI_ERR_INVALID, "gai_pan_terminal: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_pan_terminal");
 	const size_t sb = (size_t)n * 40, vb = (size_t)n * 16;
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, 3 * vb, false); EN(ctx->d_misc, 64, false);
 	int* d_v = (int*)ctx->d_out2.p;
@@ -587,6 +735,7 @@ int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves
 	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout: playouts_per_leaf must be >= 1");
 	if (eval_kind != 0 && eval_kind != 1) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout: eval_kind must be 0 (num_cards) or 1 (num_cards_weighted)");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_pan_rollout");
 	const size_t sb = (size_t)n_leaves * 40, rb = (size_t)n_leaves * sizeof(gai_pan_result);
 	EN(ctx->h_in, sb, true); EN(ctx->h_out, rb, true);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, rb, false); EN(ctx->d_misc, 64, false); EN(ctx->d_prep, (size_t)n_leaves * 32, false);
@@ -621,6 +770,7 @@ int gai_pan_playout_trace(gai_ctx* ctx, const gai_pan_state* states, uint32_t n,
 	if (n == 0) return GAI_OK;
 	if (!states || !code || !plies || !value || !final_states) return fail(ctx, GAI_ERR_INVALID, "gai_pan_playout_trace: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_pan_playout_trace");
 	const size_t sb = (size_t)n * 40;
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 20, false); EN(ctx->d_out3, sb, false); EN(ctx->d_misc, 64, false);
 	uint32_t* d_pl = (uint32_t*)ctx->d_out2.p; int* d_val = (int*)(d_pl + n);
@@ -768,6 +918,7 @@ int gai_allreduce_root(gai_ctx* ctx, uint32_t* visits, float* values, uint32_t c
 	if (count == 0) return GAI_OK;
 	if (!visits || !values) return fail(ctx, GAI_ERR_INVALID, "gai_allreduce_root: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_allreduce_root");
 	const size_t vb = (size_t)count * 4, fb = (size_t)count * 8;
 	EN(ctx->d_in, vb + fb, false);
 	char* d = (char*)ctx->d_in.p;
@@ -790,6 +941,7 @@ int gai_allreduce_u64(gai_ctx* ctx, uint64_t* v, uint32_t count)
 	if (count == 0) return GAI_OK;
 	if (!v) return fail(ctx, GAI_ERR_INVALID, "gai_allreduce_u64: NULL buffer");
 	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_allreduce_u64");
 	EN(ctx->d_in, (size_t)count * 8, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, v, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
 	NC(ctx->nccl.AllReduce(ctx->d_in.p, ctx->d_in.p, count, 5, 0, ctx->comm, ctx->stream));

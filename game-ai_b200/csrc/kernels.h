@@ -17,6 +17,8 @@ void launch_loa_playout_trace(const void* d_states, uint32_t n, uint32_t max_pli
 void launch_loa_gen_reachable(uint32_t n, uint64_t key, uint32_t max_k, void* d_boards, void* d_states24, uint8_t* d_side, cudaStream_t st);
 void launch_loa_pack_stm(const uint8_t* d_side, uint32_t n, uint32_t* d_stm, cudaStream_t st);
 void launch_loa_split_states(const void* d_states24, uint32_t n, void* d_boards, uint32_t* d_stm, cudaStream_t st);
+// all successors of n parents (reference move order) into the rollout layout: boards + one side byte per child
+void launch_loa_expand_children(const void* d_parents24, uint32_t n, const uint32_t* d_offsets, void* d_boards, uint8_t* d_side, uint32_t* d_bad, cudaStream_t st);
 
 // "rotated boards + line LUT" formulation (loa_fast.cuh): one CTA per SM, LUT in shared memory
 int  loa_fast_lut_bytes();

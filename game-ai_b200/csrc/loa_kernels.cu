@@ -225,6 +225,33 @@ __global__ void k_split_states(const u64* __restrict__ states24, u32 n, ulonglon
 	if ((threadIdx.x & 31u) == 0 && i < n) stm[i >> 5] = word;
 }
 
+// Batch-by-expansion: every successor of every parent, in reference move order, becomes a leaf.  One parent per thread
+// (a batch has ~1e3 parents, the rollout that follows ~1e6 playouts: this kernel is not on the critical path).
+// child k of parent i -> leaf offsets[i] + k; a parent whose move count differs from what the host announced sets *bad.
+__global__ void k_expand_children(const u64* __restrict__ parents24, u32 n, const u32* __restrict__ offsets,
+                                  ulonglong2* __restrict__ boards, uint8_t* __restrict__ side_out, u32* __restrict__ bad)
+{
+	__shared__ u64 s_ld[64], s_rd[64];
+	load_tables(s_ld, s_rd);
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u64 w = parents24[3 * (size_t)i], b = parents24[3 * (size_t)i + 1];
+	const u32 side = (u32)parents24[3 * (size_t)i + 2] & 1u;
+	const u64 my = side ? b : w, en = side ? w : b;
+	const MoveMasks m = all_piece_moves(my, en, s_ld, s_rd);
+	const u32 cnt = (u32)count_moves(m);
+	const u32 o0 = offsets[i], want = offsets[i + 1] - o0;
+	if (cnt != want) { atomicOr(bad, 1u); return; }
+	for (u32 k = 0; k < cnt; ++k) {
+		int from, to;
+		nth_move(m, my, en, k, s_ld, s_rd, &from, &to);
+		u64 nmy = my, nen = en;
+		apply_move(nmy, nen, from, to);
+		boards[o0 + k] = side ? make_ulonglong2(nen, nmy) : make_ulonglong2(nmy, nen);
+		side_out[o0 + k] = (uint8_t)(side ^ 1u);
+	}
+}
+
 } // namespace loa
 
 // ---------------------------------------------------------------------------------------------
@@ -257,3 +284,5 @@ void launch_loa_pack_stm(const uint8_t* d_side, uint32_t n, uint32_t* d_stm, cud
 { if (n) k_pack_stm<<<nblk(n, 256), 256, 0, st>>>(d_side, n, d_stm); }
 void launch_loa_split_states(const void* d_states24, uint32_t n, void* d_boards, uint32_t* d_stm, cudaStream_t st)
 { if (n) k_split_states<<<nblk(n, 256), 256, 0, st>>>((const u64*)d_states24, n, (ulonglong2*)d_boards, d_stm); }
+void launch_loa_expand_children(const void* d_parents24, uint32_t n, const uint32_t* d_offsets, void* d_boards, uint8_t* d_side, uint32_t* d_bad, cudaStream_t st)
+{ if (n) k_expand_children<<<nblk(n, 64), 64, 0, st>>>((const u64*)d_parents24, n, d_offsets, (ulonglong2*)d_boards, d_side, d_bad); }

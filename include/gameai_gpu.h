@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define GAI_ABI_VERSION 1
+#define GAI_ABI_VERSION 2
 
 enum gai_status {
 	GAI_OK = 0,
@@ -107,13 +107,41 @@ int gai_loa_successor_hash(gai_ctx* ctx, const gai_loa_state* states, uint32_t n
 int gai_loa_rollout(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
                     uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id,
                     gai_loa_result* out, gai_rollout_stats* stats);
-/* Asynchronous variant: enqueues H2D, kernel and D2H on the ctx stream and returns; `leaves` is copied
- * into pinned staging before return, `out` is valid after gai_sync(ctx).  One batch in flight per ctx. */
+/* Asynchronous variant: enqueues H2D, kernel and D2H on the ctx stream and returns; pageable `leaves` are copied
+ * into pinned staging before return (a PINNED `leaves` buffer is DMA-ed in place and must stay untouched until
+ * gai_sync), `out` is valid after gai_sync(ctx).  One batch in flight per ctx through this entry point; use the
+ * ticketed calls below for more. */
 int gai_loa_rollout_async(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
                           uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id, gai_loa_result* out);
 
 /* Statistics of the last rollout that completed on ctx (valid after gai_sync following gai_loa_rollout_async). */
 int gai_last_rollout_stats(gai_ctx* ctx, gai_rollout_stats* stats);
+
+/* ---- ticketed batches: several leaf batches queued on one context ---------------------------- */
+/* The host player keeps the GPU fed by selecting batch k+1 (and k+2 ...) while batch k plays out: up to
+ * GAI_MAX_INFLIGHT batches may be queued at once, each with its own staging and device buffers; they run in
+ * submission order on the context's stream.  `leaves` is copied before the call returns (pageable memory) or must
+ * stay untouched until gai_wait (pinned memory is DMA-ed in place); `out` is written by gai_wait(ticket) (pageable) or
+ * by the DMA that gai_wait waits for (pinned).  A submit with all slots busy returns GAI_ERR_INVALID.
+ * While any ticket is outstanding, the synchronous entry points of the same context (movegen / apply / terminal /
+ * Pan / allreduce / rollout_device / rollout_async) refuse to run: they share the context's scratch buffers. */
+#define GAI_MAX_INFLIGHT 4
+int gai_loa_rollout_submit(gai_ctx* ctx, const gai_loa_state* leaves, uint32_t n_leaves, uint32_t playouts_per_leaf,
+                           uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id, gai_loa_result* out, int* ticket);
+/* Batch-by-expansion: for every parent position ALL its successors (IGameRules::GetPlayerLegalMoves order,
+ * LinesOfActionZasady.cpp:167-232, generated and applied on the device) are played out playouts_per_leaf times each --
+ * what MC::Player does one simulation at a time when it first tries every move of a fresh node (all UCB values tie,
+ * MCTSPlayer.cpp:582-593).  child_offsets[n_parents + 1] (host): child k of parent i is leaf number child_offsets[i] + k,
+ * its result goes to out[child_offsets[i] + k], its playouts have ids first_playout_id + (child_offsets[i] + k) *
+ * playouts_per_leaf + j.  The caller computes the offsets from its own move lists; a parent whose device move count
+ * differs from child_offsets[i+1] - child_offsets[i] fails the batch (gai_wait returns GAI_ERR_INVALID). */
+int gai_loa_rollout_children_submit(gai_ctx* ctx, const gai_loa_state* parents, uint32_t n_parents, const uint32_t* child_offsets,
+                                    uint32_t playouts_per_leaf, uint32_t max_plies, uint64_t philox_key, uint64_t first_playout_id,
+                                    gai_loa_result* out, int* ticket);
+/* Blocks until the batch behind `ticket` has finished and its results are in `out`; stats may be NULL. */
+int gai_wait(gai_ctx* ctx, int ticket, gai_rollout_stats* stats);
+/* number of tickets outstanding on ctx */
+int gai_inflight(const gai_ctx* ctx);
 
 /* DEVICE-resident variant (inputs already in HBM).  d_boards: n_leaves x {white,black} (16 B each,
  * 16-byte aligned); d_stm: ceil(n/32) words, bit (i&31) of word i>>5 = side to move of leaf i;

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version():
-    assert g.lib().gai_abi_version() == 1
+    assert g.lib().gai_abi_version() == 2
 
 
 def test_struct_layouts_match_reference():

@@ -61,7 +61,7 @@ def test_determinized_gpu_pan_player_beats_lowcard():
 def test_tree_reuse_and_gc():
     # a long search per move grows the tree past the GC threshold; the root of the next decision is found in the old
     # tree (reference: findRootNode, MCTSPlayer.cpp:219-251) and unreachable nodes are freed
-    res = run("--p1", "mcts move_sim_limit=2000000 gpu_batch=2048 playouts_per_leaf=8 random_seed=51 philox_seed=52", "--p2", "random random_seed=53", "--ng", "1", "--seed", "12")
+    res = run("--p1", "mcts move_sim_limit=2000000 gpu_batch=2048 playouts_per_leaf=8 expand_all=0 random_seed=51 philox_seed=52", "--p2", "random random_seed=53", "--ng", "1", "--seed", "12")
     st = res["players"][0]["stats"]
     assert float(st["reused_root_visits"]) > 0 and float(st["tree_gc_runs"]) >= 1 and float(st["tree_gc_freed_nodes"]) > 0
     assert res["players"][0]["lose"] == 0

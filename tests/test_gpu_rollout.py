@@ -153,3 +153,56 @@ def test_async_rollout_matches_sync(gpu, oracle):
     gpu.sync()
     st = gpu.last_rollout_stats()
     assert (out == sync_counts).all() and st["plies"] == sync_st["plies"] and st["playouts"] == sync_st["playouts"]
+
+
+# ---- ticketed batches (several queued per context) and batch-by-expansion ------------------------------------------
+def _children_by_oracle(oracle, P):
+    """all successors of every parent in reference move order -> (children (m,3), offsets (n+1,))"""
+    cnt, mv = oracle.movegen_batch(P)
+    kids, off = [], [0]
+    for i in range(len(P)):
+        n = int(cnt[i])
+        if n:
+            kids.append(oracle.apply_batch(np.repeat(P[i:i + 1], n, axis=0), mv[i, :n]))
+        off.append(off[-1] + n)
+    return (np.concatenate(kids) if kids else np.zeros((0, 3), np.uint64)), np.array(off, np.uint32)
+
+
+def test_ticketed_batches_queue_and_match_oracle(gpu, oracle):
+    import gameai_b200 as g
+    batches = [oracle.gen_reachable(700 + 100 * k, 100 + k) for k in range(4)]
+    outs = [np.zeros((len(b), 4), np.uint32) for b in batches]
+    tickets = [gpu.submit(b, o, 3, 50000, 0xABCD + k, 1000 * k) for k, (b, o) in enumerate(zip(batches, outs))]
+    assert gpu.inflight() == 4
+    with pytest.raises(g.GaiError):                                # a fifth batch has no slot
+        gpu.submit(batches[0], np.zeros((len(batches[0]), 4), np.uint32), 3, 50000, 1, 0)
+    with pytest.raises(g.GaiError):                                # the synchronous calls refuse while tickets are out
+        gpu.movegen(batches[0][:4])
+    for k in (2, 0, 3, 1):                                         # any order
+        st = gpu.wait(tickets[k])
+        oc, opl = oracle.rollout_states(batches[k], 3, 50000, 0xABCD + k, 1000 * k)
+        assert (outs[k] == oc).all() and st["plies"] == opl and st["playouts"] == 3 * len(batches[k])
+    assert gpu.inflight() == 0
+    with pytest.raises(g.GaiError):
+        gpu.wait(tickets[0])                                       # stale ticket
+    c, _ = gpu.movegen(batches[0][:4])                             # the context is usable again
+    assert c.shape == (4,)
+
+
+def test_children_expansion_vs_oracle(gpu, oracle):
+    import gameai_b200 as g
+    P = np.concatenate([oracle.gen_reachable(300, 5), oracle.gen_uniform(100, 6)])
+    kids, off = _children_by_oracle(oracle, P)
+    out = np.zeros((len(kids), 4), np.uint32)
+    t = gpu.submit_children(P, off, out, 2, 50000, 0x77, 555)
+    st = gpu.wait(t)
+    oc, opl = oracle.rollout_states(kids, 2, 50000, 0x77, 555)
+    assert (out == oc).all() and st["plies"] == opl and st["playouts"] == 2 * len(kids)
+    # a wrong child count is caught on the device
+    bad = off.copy(); bad[1:] += 1
+    t = gpu.submit_children(P, bad, np.zeros((int(bad[-1]), 4), np.uint32), 1, 10, 1, 0)
+    with pytest.raises(g.GaiError):
+        gpu.wait(t)
+    # empty batch
+    t = gpu.submit_children(np.zeros((0, 3), np.uint64), np.zeros(1, np.uint32), np.zeros((0, 4), np.uint32), 1, 10, 1, 0)
+    assert gpu.wait(t)["playouts"] == 0

@@ -38,7 +38,7 @@ def test_values_and_choice_vs_reference_player(pos, oracle):
     sims = 1536
     r = ref.select(w, b, cp, sims, seed=77)
     me, other = ("mcts", "random") if cp == 0 else ("random", "mcts")
-    spec = "mcts move_sim_limit=%d gpu_batch=48 playouts_per_leaf=1 random_seed=5 philox_seed=11" % sims
+    spec = "mcts move_sim_limit=%d gpu_batch=48 playouts_per_leaf=1 expand_all=0 random_seed=5 philox_seed=11" % sims
     args = [LAUNCHER, "--xml", XML, "--p1", spec if cp == 0 else "random", "--p2", spec if cp == 1 else "random",
             "--ng", "1", "--rl", "1", "--start", "%d,%d,%d" % (w, b, cp)]
     out = subprocess.run(args, capture_output=True, text=True, timeout=300)
