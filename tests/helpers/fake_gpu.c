@@ -2,7 +2,9 @@
  * CPU through the oracle (oracle/libloa_oracle.so).  It exists so that the HOST logic of the GPU-backed player
  * (selection, virtual loss, batch-by-expansion, pipelining, back-propagation, config keys, statistics) can be exercised by
  * `pytest -m "not gpu"` without a device: tests LD_PRELOAD it under GameLauncher.  Nothing in the product loads it; the
- * real library has no CPU path (tests/test_abi.py::test_no_cpu_fallback). */
+ * real library has no CPU path (tests/test_abi.py::test_no_cpu_fallback).
+ * GAI_FAKE_MODE=hash: no games are played at all -- every leaf "returns" a deterministic pseudo-random split of its
+ * playouts (a hash of the position), for tests that need many simulations (tree growth, garbage collection) quickly. */
 #include "gameai_gpu.h"
 #include "../../oracle/loa_oracle.h"
 #include <stdlib.h>
@@ -19,8 +21,19 @@ uint64_t gai_launch_count(const gai_ctx* c) { return c->launches; }
 
 static int slot_of(gai_ctx* c) { for (int i = 0; i < GAI_MAX_INFLIGHT; ++i) if (!c->busy[i]) return i; return -1; }
 
+static uint64_t mix(uint64_t h) { h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31; return h; }
 static void play(gai_ctx* c, int s, const uint64_t* st, uint32_t n, uint32_t ppl, uint32_t max_plies, uint64_t key, uint64_t first_id, gai_loa_result* out)
 {
+	const char* mode = getenv("GAI_FAKE_MODE");
+	if (mode && !strcmp(mode, "hash")) {
+		for (uint32_t i = 0; i < n; ++i) {
+			const uint64_t h = mix(st[3 * i] ^ mix(st[3 * i + 1] ^ (st[3 * i + 2] & 1)));
+			const uint32_t ww = (uint32_t)(((h & 0xffff) * (ppl + 1)) >> 16);            /* uniform in [0, ppl] */
+			out[i].white_wins = ww; out[i].black_wins = ppl - ww; out[i].draws = 0; out[i].capped = 0;
+		}
+		c->playouts[s] = (uint64_t)n * ppl; c->plies[s] = c->playouts[s] * 100; c->launches += 3;
+		return;
+	}
 	uint64_t* w = (uint64_t*)malloc(8 * (size_t)(n ? n : 1)); uint64_t* b = (uint64_t*)malloc(8 * (size_t)(n ? n : 1)); uint8_t* cp = (uint8_t*)malloc(n ? n : 1);
 	for (uint32_t i = 0; i < n; ++i) { w[i] = st[3 * i]; b[i] = st[3 * i + 1]; cp[i] = (uint8_t)(st[3 * i + 2] & 1); }
 	memset(out, 0, sizeof(gai_loa_result) * (size_t)n);

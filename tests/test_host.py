@@ -65,18 +65,21 @@ def test_gpu_player_refuses_to_play_without_a_gpu():
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
-# ---- host logic of the GPU MCTS player with the GPU library replaced by a TEST stub (LD_PRELOAD, tests/helpers/fake_gpu.cpp) ----
+# ---- host logic of the GPU MCTS player with the GPU library replaced by a TEST stub (LD_PRELOAD, tests/helpers/fake_gpu.c in
+# its "hash" mode: no games are played, every leaf gets a pseudo-random split of its playouts; tests/test_player_host.py uses
+# the same stub with real (oracle) playouts) ----
 @pytest.fixture(scope="module")
 def fake_gpu():
-    so = os.path.join(ROOT, "tests", "helpers", "libfake_gpu.so")
-    src = os.path.join(ROOT, "tests", "helpers", "fake_gpu.cpp")
+    so = os.path.join(ROOT, "tests", "helpers", "libfakegpu.so")
+    src = os.path.join(ROOT, "tests", "helpers", "fake_gpu.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, src])
+        subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, src,
+                               "-L", os.path.join(ROOT, "oracle"), "-lloa_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     return so
 
 
 def run_with_fake_gpu(fake_gpu, *args):
-    env = dict(os.environ, LD_PRELOAD=fake_gpu)
+    env = dict(os.environ, LD_PRELOAD=fake_gpu, GAI_FAKE_MODE="hash")
     r = subprocess.run([LAUNCHER, "--xml", XML] + list(args), capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     return json.loads(r.stdout.strip().splitlines()[-1])
@@ -85,7 +88,7 @@ def run_with_fake_gpu(fake_gpu, *args):
 def test_mcts_host_logic_is_deterministic_and_reuses_its_tree(fake_gpu):
     """Selection with virtual loss, lazy expansion, two pipelined batches, transposition table, tree reuse and GC, final-move
     rule -- everything above the C ABI, with fixed seeds and a simulation budget: two runs must agree move for move."""
-    args = ("--p1", "mcts move_sim_limit=400000 gpu_batch=512 playouts_per_leaf=8 random_seed=3 philox_seed=4", "--p2", "random random_seed=5",
+    args = ("--p1", "mcts move_sim_limit=400000 gpu_batch=512 playouts_per_leaf=8 expand_all=0 random_seed=3 philox_seed=4", "--p2", "random random_seed=5",
             "--ng", "1", "--rl", "40", "--seed", "6")
     a = run_with_fake_gpu(fake_gpu, *args); b = run_with_fake_gpu(fake_gpu, *args)
     assert a["rounds"] == b["rounds"] and a["first_move"] == b["first_move"]
