@@ -241,7 +241,11 @@ __global__ void k_expand_children(const u64* __restrict__ parents24, u32 n, cons
 	const MoveMasks m = all_piece_moves(my, en, s_ld, s_rd);
 	const u32 cnt = (u32)count_moves(m);
 	const u32 o0 = offsets[i], want = offsets[i + 1] - o0;
-	if (cnt != want) { atomicOr(bad, 1u); return; }
+	if (cnt != want) {                          // caller and device disagree: flag the batch, hand the rollout harmless (terminal) leaves
+		atomicOr(bad, 1u);
+		for (u32 k = 0; k < want; ++k) { boards[o0 + k] = make_ulonglong2(1ull, 2ull); side_out[o0 + k] = 0; }
+		return;
+	}
 	for (u32 k = 0; k < cnt; ++k) {
 		int from, to;
 		nth_move(m, my, en, k, s_ld, s_rd, &from, &to);

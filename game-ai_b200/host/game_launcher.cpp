@@ -16,6 +16,10 @@
 #include <dlfcn.h>
 #include <fstream>
 #include <iostream>
+#include <mutex>
+#include <thread>
+#include <atomic>
+#include <map>
 #include <random>
 #include <set>
 #include <sstream>
@@ -62,12 +66,15 @@ struct Rng : IRandomGenerator {
 	void release() override { delete this; }
 };
 
-static void* load_plugin(const std::string& provider, const std::string& dir)
+// `dirs`: colon-separated list of directories searched in order (the launcher's own directory first, then --plugins)
+static void* load_plugin(const std::string& provider, const std::string& dirs)
 {
 	std::string lower = provider; std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
-	for (const std::string& nm : { dir + "/lib" + provider + ".so", dir + "/lib" + lower + ".so", "lib" + provider + ".so", "lib" + lower + ".so" }) {
-		if (void* h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL)) return h;
-	}
+	std::vector<std::string> names;
+	std::istringstream ds(dirs); std::string dir;
+	while (std::getline(ds, dir, ':')) if (!dir.empty()) { names.push_back(dir + "/lib" + provider + ".so"); names.push_back(dir + "/lib" + lower + ".so"); }
+	names.push_back("lib" + provider + ".so"); names.push_back("lib" + lower + ".so");
+	for (const std::string& nm : names) if (void* h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL)) return h;
 	std::fprintf(stderr, "cannot load plugin '%s': %s\n", provider.c_str(), dlerror());
 	return nullptr;
 }
@@ -76,6 +83,7 @@ enum class SingleGameResult { Win = 0, RoundLimit = 1, StateLoop = 2 };
 
 // GameController.cpp:27-115
 static std::string g_first_move;      // text of the first move made in the last game (used by --rl 1 probes)
+static std::mutex g_io;                // stdout lines and g_first_move (several controller threads)
 static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlayer*>& players, GameState* state, int round_limit, int score[], int verbose, int* rounds_out)
 {
 	const int np = (int)players.size();
@@ -89,7 +97,7 @@ static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlay
 		for (int i = 0; i < np; ++i) moves[i] = players[i]->selectMove(pks[i]);
 		if (round == 0) {
 			const int cp0 = rules->GetCurrentPlayer(state);
-			if (rules->GetNumMoves(moves[cp0]) > 0) { auto [mv0, p0] = rules->GetMoveFromList(moves[cp0], 0); (void)p0; g_first_move = rules->ToString(mv0); }
+			if (rules->GetNumMoves(moves[cp0]) > 0) { auto [mv0, p0] = rules->GetMoveFromList(moves[cp0], 0); (void)p0; std::lock_guard<std::mutex> lk(g_io); g_first_move = rules->ToString(mv0); }
 		}
 		if (verbose) {
 			const int cp = rules->GetCurrentPlayer(state);
@@ -119,11 +127,31 @@ static SingleGameResult run_single_game(IGameRules* rules, std::vector<IGamePlay
 	return result;
 }
 
+// mergeResults (common/api/GameController.h:41): histograms and averages add up, numbers add, text keeps the last value
+static void merge_metrics(NamedMetrics_t& into, const NamedMetrics_t& from)
+{
+	for (auto& kv : from) {
+		auto it = into.find(kv.first);
+		if (it == into.end()) { into[kv.first] = kv.second; continue; }
+		if (auto h = std::get_if<Histogram<long>>(&kv.second)) { if (auto d = std::get_if<Histogram<long>>(&it->second)) *d += *h; }
+		else if (auto a = std::get_if<Average>(&kv.second)) { if (auto d = std::get_if<Average>(&it->second)) *d += *a; }
+		else if (auto x = std::get_if<double>(&kv.second)) { if (auto d = std::get_if<double>(&it->second)) *d += *x; }
+		else it->second = kv.second;
+	}
+}
+static std::string xml_escape(const std::string& s)
+{
+	std::string o;
+	for (char c : s) { if (c == '&') o += "&amp;"; else if (c == '<') o += "&lt;"; else if (c == '>') o += "&gt;"; else if (c == '"') o += "&quot;"; else o += c; }
+	return o;
+}
+
 int main(int argc, char** argv)
 {
-	std::string xml = "run_config_loa.xml", plugin_dir;
+	std::string xml = "run_config_loa.xml", plugin_dir, save_file;
 	std::vector<std::string> pnames(4);
-	int num_games = -1, round_limit = -1, verbose = 0;
+	int num_games = -1, round_limit = -1, verbose = 0, num_threads = -1;
+	bool progress = false, quiet = false;
 	std::string start_hash;
 	unsigned seed = 12345;
 	{	// plugins live next to the executable
@@ -136,11 +164,15 @@ int main(int argc, char** argv)
 		else if (a == "--p1" || a == "--p2" || a == "--p3" || a == "--p4") pnames[a[3] - '1'] = next();
 		else if (a == "--ng") num_games = atoi(next().c_str());
 		else if (a == "--rl") round_limit = atoi(next().c_str());
+		else if (a == "--threads" || a == "-t") num_threads = atoi(next().c_str());           // GameLauncher.cpp:152
+		else if (a == "--progress" || a == "-p") progress = true;                           // :145
+		else if (a == "--quiet" || a == "-q") quiet = true;                                 // :153
+		else if (a == "--save") save_file = next();
 		else if (a == "--seed") seed = (unsigned)strtoul(next().c_str(), nullptr, 10);
 		else if (a == "--verbose" || a == "-v") verbose = 1;
-		else if (a == "--plugins") plugin_dir = next();
+		else if (a == "--plugins") plugin_dir += ":" + next();                              // extra plugin directories (colon separated)
 		else if (a == "--start") start_hash = next();      // "white,black,cp" as hex/decimal words: play from this position
-		else if (a == "--help" || a == "-h") { std::printf("usage: GameLauncher --xml cfg.xml --p1 \"name [key=value ...]\" --p2 name [--ng N] [--rl N] [--seed S] [-v]\n"); return 0; }
+		else if (a == "--help" || a == "-h") { std::printf("usage: GameLauncher --xml cfg.xml --p1 \"name [key=value ...]\" --p2 name [--ng N] [--rl N] [--threads N] [--seed S] [--save results.xml] [-v] [-p] [-q]\n"); return 0; }
 	}
 	std::ifstream f(xml);
 	if (!f) { std::fprintf(stderr, "cannot open %s\n", xml.c_str()); return 2; }
@@ -150,6 +182,13 @@ int main(int argc, char** argv)
 	for (auto& e : elems) { if (e.tag == "game") game = e.attrs; else if (e.tag == "player") player_defs.push_back(e.attrs); }
 	if (num_games < 0) num_games = game.get_optional<int>("num_games").get_value_or(1);
 	if (round_limit < 0) round_limit = game.get_optional<int>("round_limit").get_value_or(300);
+	if (num_threads < 0) num_threads = game.get_optional<int>("num_threads").get_value_or(1);       // GameController.cpp:122
+	num_threads = std::max(1, std::min(num_threads, std::max(1, num_games)));
+	if (save_file.empty()) save_file = game.get_optional<std::string>("save").get_value_or("");      // run_config_loa.xml:3 save="results.xml"
+	if (!save_file.empty() && save_file.find('/') == std::string::npos) {
+		const std::string od = game.get_optional<std::string>("out_dir").get_value_or("");
+		if (!od.empty() && od.find('\\') == std::string::npos) save_file = od + "/" + save_file;     // a Windows path from the reference's XML is not a directory here
+	}
 
 	void* hr = load_plugin(game.get<std::string>("provider"), plugin_dir);
 	if (!hr) return 3;
@@ -171,59 +210,125 @@ int main(int argc, char** argv)
 	}
 	const int np = (int)pcfg.size();
 	if (np < 2) { std::fprintf(stderr, "need at least --p1 and --p2\n"); return 2; }
+	std::vector<CreatePlayer_t> factories;
+	for (int i = 0; i < np; ++i) {
+		pcfg[i].put("number_of_players", np);                                        // GameController.cpp:152-155
+		void* hp = load_plugin(pcfg[i].get<std::string>("provider"), plugin_dir);
+		if (!hp) return 3;
+		auto create_player = (CreatePlayer_t)dlsym(hp, "createPlayer");
+		if (!create_player) { std::fprintf(stderr, "plugin lacks createPlayer\n"); return 3; }
+		factories.push_back(create_player);
+	}
 
-	IGameRules* rules = create_rules(np);
-	Rng* rng = new Rng(seed);
-	std::vector<IGamePlayer*> players;
-	try {
-		for (int i = 0; i < np; ++i) {
-			pcfg[i].put("number_of_players", np);                                        // GameController.cpp:152-155
-			if (!pcfg[i].get_optional<unsigned>("random_seed")) pcfg[i].put("random_seed", seed + 1000u * (unsigned)(i + 1));
-			void* hp = load_plugin(pcfg[i].get<std::string>("provider"), plugin_dir);
-			if (!hp) return 3;
-			auto create_player = (CreatePlayer_t)dlsym(hp, "createPlayer");
-			if (!create_player) { std::fprintf(stderr, "plugin lacks createPlayer\n"); return 3; }
-			IGamePlayer* p = create_player(i, &pcfg[i]);
-			p->setGameRules(rules);
-			players.push_back(p);
-		}
-	} catch (const char* msg) { std::fprintf(stderr, "error: %s\n", msg); return 4; }
-
+	// results of the whole run (merged under a mutex, GameController.cpp:208-210)
+	std::mutex mtx;
 	std::vector<double> pts(np, 0); std::vector<int> wins(np, 0), loses(np, 0);
-	int aborted = 0; long rounds_total = 0;
+	std::vector<NamedMetrics_t> stats((size_t)np); std::vector<std::string> names((size_t)np);
+	std::map<std::string, int> game_results;
+	int aborted = 0; long rounds_total = 0; int failed = 0; std::string failure;
+	std::atomic<int> games_done{ 0 };
 	const auto t0 = std::chrono::steady_clock::now();
-	try {
-		for (int g = 0; g < num_games; ++g) {
-			int score[4] = { 0, 0, 0, 0 }, rounds = 0;
-			GameState* st;
-			if (start_hash.empty()) st = rules->CreateRandomInitialState(rng);
-			else {
-				uint64_t wds[3] = { 0, 0, 0 }; char* e = nullptr; const char* q = start_hash.c_str();
-				for (int k = 0; k < 3; ++k) { wds[k] = strtoull(q, &e, 0); q = (*e == ',') ? e + 1 : e; }
-				st = rules->CreateInitialStateFromHash(reinterpret_cast<const uint32_t*>(wds));       // LOA: the 24-byte state is its own hash
+
+	// one controller thread = its own rules object, players (a GPU player: its own gai_ctx) and generator, never shared
+	// (GameController.cpp:167-204); the games are split evenly, the first threads take the remainder
+	auto worker = [&](int instance) {
+		const int my_games = num_games / num_threads + (instance < num_games % num_threads ? 1 : 0);
+		IGameRules* rules = create_rules(np);
+		Rng* rng = new Rng(seed + 7919u * (unsigned)instance);
+		std::vector<IGamePlayer*> players;
+		std::vector<double> t_pts(np, 0); std::vector<int> t_wins(np, 0), t_loses(np, 0);
+		std::map<std::string, int> t_results; int t_aborted = 0; long t_rounds = 0;
+		try {
+			for (int i = 0; i < np; ++i) {
+				Config c = pcfg[i];
+				if (!c.get_optional<unsigned>("random_seed")) c.put("random_seed", seed + 1000u * (unsigned)(i + 1) + 7919u * (unsigned)instance);
+				else if (instance > 0) c.put("random_seed", c.get<unsigned>("random_seed") + 7919u * (unsigned)instance);      // threads must not replay each other's games
+				IGamePlayer* p = factories[i](i, &c);
+				p->setGameRules(rules);
+				players.push_back(p);
 			}
-			const SingleGameResult r = run_single_game(rules, players, st, round_limit, score, verbose, &rounds);
-			rounds_total += rounds;
-			if (r != SingleGameResult::Win) ++aborted;
-			for (int i = 0; i < np; ++i) { pts[i] += score[i]; if (r == SingleGameResult::Win) { if (score[i] == 0) ++loses[i]; else if (!(np == 2 && score[i] == 50)) ++wins[i]; } }
-			std::printf("game %d: %s after %d rounds, score", g + 1, r == SingleGameResult::Win ? "finished" : r == SingleGameResult::RoundLimit ? "round limit" : "state loop", rounds);
-			for (int i = 0; i < np; ++i) std::printf(" %s=%d", players[i]->getName().c_str(), score[i]);
-			std::printf("\n"); std::fflush(stdout);
+			for (int g = 0; g < my_games; ++g) {
+				int score[4] = { 0, 0, 0, 0 }, rounds = 0;
+				GameState* st;
+				if (start_hash.empty()) st = rules->CreateRandomInitialState(rng);
+				else {
+					uint64_t wds[3] = { 0, 0, 0 }; char* e = nullptr; const char* q = start_hash.c_str();
+					for (int k = 0; k < 3; ++k) { wds[k] = strtoull(q, &e, 0); q = (*e == ',') ? e + 1 : e; }
+					st = rules->CreateInitialStateFromHash(reinterpret_cast<const uint32_t*>(wds));       // LOA: the 24-byte state is its own hash
+				}
+				const SingleGameResult r = run_single_game(rules, players, st, round_limit, score, verbose && num_threads == 1, &rounds);
+				t_rounds += rounds;
+				if (r != SingleGameResult::Win) ++t_aborted;
+				t_results[r == SingleGameResult::Win ? "Win" : r == SingleGameResult::RoundLimit ? "RoundLimit" : "StateLoop"] += 1;       // singleRunResultString
+				for (int i = 0; i < np; ++i) { t_pts[i] += score[i]; if (r == SingleGameResult::Win) { if (score[i] == 0) ++t_loses[i]; else if (!(np == 2 && score[i] == 50)) ++t_wins[i]; } }
+				const int done = ++games_done;
+				std::lock_guard<std::mutex> lk(g_io);
+				if (!quiet) {
+					std::printf("game %d: %s after %d rounds, score", done, r == SingleGameResult::Win ? "finished" : r == SingleGameResult::RoundLimit ? "round limit" : "state loop", rounds);
+					for (int i = 0; i < np; ++i) std::printf(" %s=%d", players[i]->getName().c_str(), score[i]);
+					std::printf("\n"); std::fflush(stdout);
+				}
+				if (progress) {                                                               // createProgressBar(total_progress, number_of_games, type)
+					const int w = 40, fill = (int)((long)w * done / std::max(1, num_games));
+					std::fprintf(stderr, "\r[%.*s%*s] %d/%d", fill, "########################################", w - fill, "", done, num_games);
+					if (done == num_games) std::fprintf(stderr, "\n");
+					std::fflush(stderr);
+				}
+			}
+		} catch (const char* msg) { std::lock_guard<std::mutex> lk(mtx); ++failed; failure = msg; }
+		  catch (const std::exception& e) { std::lock_guard<std::mutex> lk(mtx); ++failed; failure = e.what(); }
+		{
+			std::lock_guard<std::mutex> lk(mtx);
+			for (int i = 0; i < np && i < (int)players.size(); ++i) {
+				pts[i] += t_pts[i]; wins[i] += t_wins[i]; loses[i] += t_loses[i];
+				merge_metrics(stats[(size_t)i], players[i]->getGameStats());               // appendPlayerStats
+				names[(size_t)i] = players[i]->getName();
+			}
+			for (auto& kv : t_results) game_results[kv.first] += kv.second;
+			aborted += t_aborted; rounds_total += t_rounds;
 		}
-	} catch (const char* msg) { std::fprintf(stderr, "error: %s\n", msg); return 4; }
+		for (auto* p : players) p->release();
+		rules->Release();
+		rng->release();
+	};
+	if (num_threads == 1) worker(0);
+	else {
+		std::vector<std::thread> th;
+		for (int i = 0; i < num_threads; ++i) th.emplace_back(worker, i);
+		for (auto& t : th) t.join();
+	}
+	if (failed) { std::fprintf(stderr, "error: %s\n", failure.c_str()); return 4; }
 	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
-	// results (the reference writes the same fields to results.xml: pN.pts / pN.win / pN.lose + player metrics, GameController.cpp:101-111,199)
-	std::printf("{\"games\": %d, \"aborted\": %d, \"rounds\": %ld, \"seconds\": %.3f, \"first_move\": \"%s\", \"players\": [", num_games, aborted, rounds_total, secs, g_first_move.c_str());
+	// results.xml (saveXmlResults; the reference stores pN.pts / pN.win / pN.lose, num_rounds, num_games, game_results and the
+	// players' metrics as attributes, GameController.cpp:101-111,199,213-215)
+	if (!save_file.empty()) {
+		std::ofstream o(save_file);
+		if (!o) std::fprintf(stderr, "cannot write %s\n", save_file.c_str());
+		else {
+			o << "<?xml version=\"1.0\" encoding=\"utf-8\"?>\n<results num_games=\"" << num_games << "\" num_rounds=\"" << rounds_total << "\" num_threads=\"" << num_threads
+			  << "\" time_s=\"" << secs << "\" game_results=\"";
+			bool first = true;
+			for (auto& kv : game_results) { o << (first ? "" : ",") << kv.first << ":" << kv.second; first = false; }
+			o << "\"";
+			for (int i = 0; i < np; ++i) o << " p" << i + 1 << ".pts=\"" << pts[i] << "\" p" << i + 1 << ".win=\"" << wins[i] << "\" p" << i + 1 << ".lose=\"" << loses[i] << "\"";
+			o << ">\n";
+			for (int i = 0; i < np; ++i) {
+				o << "  <p" << i + 1 << " name=\"" << xml_escape(names[(size_t)i]) << "\"";
+				for (auto& kv : stats[(size_t)i]) o << " " << kv.first << "=\"" << xml_escape(metric_to_string(kv.second)) << "\"";
+				o << " />\n";
+			}
+			o << "</results>\n";
+		}
+	}
+
+	std::printf("{\"games\": %d, \"aborted\": %d, \"rounds\": %ld, \"seconds\": %.3f, \"threads\": %d, \"first_move\": \"%s\", \"players\": [", num_games, aborted, rounds_total, secs, num_threads, g_first_move.c_str());
 	for (int i = 0; i < np; ++i) {
-		std::printf("%s{\"name\": \"%s\", \"pts\": %.1f, \"win\": %d, \"lose\": %d, \"stats\": {", i ? ", " : "", players[i]->getName().c_str(), pts[i], wins[i], loses[i]);
+		std::printf("%s{\"name\": \"%s\", \"pts\": %.1f, \"win\": %d, \"lose\": %d, \"stats\": {", i ? ", " : "", names[(size_t)i].c_str(), pts[i], wins[i], loses[i]);
 		bool first = true;
-		for (auto& kv : players[i]->getGameStats()) { std::printf("%s\"%s\": \"%s\"", first ? "" : ", ", kv.first.c_str(), metric_to_string(kv.second).c_str()); first = false; }
+		for (auto& kv : stats[(size_t)i]) { std::printf("%s\"%s\": \"%s\"", first ? "" : ", ", kv.first.c_str(), metric_to_string(kv.second).c_str()); first = false; }
 		std::printf("}}");
 	}
 	std::printf("]}\n");
-	for (auto* p : players) p->release();
-	rules->Release();
-	rng->release();
 	return 0;
 }

@@ -200,9 +200,11 @@ def test_children_expansion_vs_oracle(gpu, oracle):
     assert (out == oc).all() and st["plies"] == opl and st["playouts"] == 2 * len(kids)
     # a wrong child count is caught on the device
     bad = off.copy(); bad[1:] += 1
-    t = gpu.submit_children(P, bad, np.zeros((int(bad[-1]), 4), np.uint32), 1, 10, 1, 0)
+    out_bad = np.zeros((int(bad[-1]), 4), np.uint32)               # (kept alive until wait: the library writes into it)
+    t = gpu.submit_children(P, bad, out_bad, 1, 10, 1, 0)
     with pytest.raises(g.GaiError):
         gpu.wait(t)
     # empty batch
-    t = gpu.submit_children(np.zeros((0, 3), np.uint64), np.zeros(1, np.uint32), np.zeros((0, 4), np.uint32), 1, 10, 1, 0)
+    P0, off0, out0 = np.zeros((0, 3), np.uint64), np.zeros(1, np.uint32), np.zeros((0, 4), np.uint32)
+    t = gpu.submit_children(P0, off0, out0, 1, 10, 1, 0)
     assert gpu.wait(t)["playouts"] == 0
