@@ -119,7 +119,9 @@ int enqueue_rollout(gai_ctx* ctx, Buf& misc, Buf& prep, cudaEvent_t ev_k0, cudaE
 	EN(misc, 128, false);
 	// d_prep: [n x 64 B rotations][n x u32 order][n x u8 piece counts][64 x u32 histogram + cursors]
 	const size_t prep_b = (size_t)n_leaves * 64, ord_b = (size_t)n_leaves * 4, pc_b = ((size_t)n_leaves + 255) / 256 * 256;
-	if (ctx->impl >= 1) EN(prep, prep_b + ord_b + pc_b + 256, false);
+	const size_t chi_b = (size_t)n_leaves * 2;
+	if (n_leaves >= (1u << 30)) return fail(ctx, GAI_ERR_INVALID, "at most 2^30 - 1 leaves per batch");
+	if (ctx->impl >= 1) EN(prep, prep_b + ord_b + pc_b + 256 + chi_b, false);
 	CU(cudaMemsetAsync(misc.p, 0, 64, ctx->stream));
 	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_loa_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
@@ -128,10 +130,11 @@ int enqueue_rollout(gai_ctx* ctx, Buf& misc, Buf& prep, cudaEvent_t ev_k0, cudaE
 		// rotations of every leaf, once per batch (inside the timed region: it is part of the step)
 		char* pb = (char*)prep.p;
 		uint32_t* d_order = (uint32_t*)(pb + prep_b); uint8_t* d_pc = (uint8_t*)(pb + prep_b + ord_b); uint32_t* d_hist = (uint32_t*)(pb + prep_b + ord_b + pc_b);
+		uint16_t* d_chi = (uint16_t*)(pb + prep_b + ord_b + pc_b + 256);
 		CU(cudaMemsetAsync(d_hist, 0, 256, ctx->stream));
-		launch_loa_prepare_leaves(d_boards, n_leaves, pb, d_pc, d_hist, d_order, ctx->stream);
+		launch_loa_prepare_leaves(d_boards, n_leaves, pb, d_pc, d_hist, d_order, d_chi, ctx->stream);
 		LAUNCHED("k_prepare_leaves"); ctx->launches += 1;      // + k_order_leaves
-		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
+		launch_loa_rollout_fast(ctx->d_lut, pb, d_stm, d_order, d_chi, n_leaves, ppl, max_plies, key, first_id, (uint32_t*)d_out,
 		                        (uint64_t*)misc.p, (unsigned long long*)misc.p + 2,
 		                        ctx->impl == 2 ? ctx->sweep_threads : ctx->fast_threads, ctx->prop.multiProcessorCount, ctx->impl == 2 ? ctx->sweep_unroll : 0, ctx->stream);
 	} else
@@ -606,7 +609,10 @@ int gai_loa_playout_trace(gai_ctx* ctx, const gai_loa_state* states, uint32_t n,
 	const size_t sb = (size_t)n * sizeof(gai_loa_state);
 	EN(ctx->d_in, sb, false); EN(ctx->d_out, n, false); EN(ctx->d_out2, (size_t)n * 4, false); EN(ctx->d_out3, sb, false);
 	CU(cudaMemcpyAsync(ctx->d_in.p, states, sb, cudaMemcpyHostToDevice, ctx->stream));
-	if (ctx->impl >= 1)
+	if (ctx->impl == 2)          // the static-sweep step itself (sweep + select + apply with chi + chi-gated flood fill)
+		launch_loa_playout_trace_sweep(ctx->d_lut, ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
+		                               (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->prop.multiProcessorCount, ctx->stream);
+	else if (ctx->impl == 1)
 		launch_loa_playout_trace_fast(ctx->d_lut, ctx->d_in.p, n, max_plies, philox_key, first_playout_id, (uint8_t*)ctx->d_out.p,
 		                              (uint32_t*)ctx->d_out2.p, ctx->d_out3.p, ctx->prop.multiProcessorCount, ctx->stream);
 	else

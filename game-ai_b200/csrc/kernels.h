@@ -24,12 +24,15 @@ void launch_loa_expand_children(const void* d_parents24, uint32_t n, const uint3
 int  loa_fast_lut_bytes();
 void loa_fast_build_lut_host(uint16_t* lut);
 cudaError_t loa_fast_prepare();
-void launch_loa_rollout_fast(const void* d_lut, const void* d_prep, const uint32_t* d_stm, const uint32_t* d_order, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+void launch_loa_rollout_fast(const void* d_lut, const void* d_prep, const uint32_t* d_stm, const uint32_t* d_order, const uint16_t* d_chi, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
                              uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
                              int threads, int sms, int sweep, cudaStream_t st);
 void launch_loa_movegen_sweep(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st);
-// 16 B boards -> 64 B rotations + the descending-piece-count order (d_hist: 64 words, zeroed by the caller)
-void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, uint8_t* d_pcount, uint32_t* d_hist, uint32_t* d_order, cudaStream_t st);
+// 16 B boards -> 64 B rotations + the descending-piece-count order (d_hist: 64 words, zeroed by the caller) + the Euler
+// characteristic of both colours (d_chi: one u16 per leaf)
+void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, uint8_t* d_pcount, uint32_t* d_hist, uint32_t* d_order, uint16_t* d_chi, cudaStream_t st);
+void launch_loa_playout_trace_sweep(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
+                                    uint8_t* d_outcome, uint32_t* d_plies, void* d_final, int sms, cudaStream_t st);
 void launch_loa_movegen_fast(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st);
 void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uint32_t n, uint64_t* d_hash, uint32_t* d_bad, int sms, cudaStream_t st);
 void launch_loa_playout_trace_fast(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,

@@ -28,6 +28,7 @@
 //    indexed by the two nibbles, replicated once per lane so that lane L only ever touches bank L: no conflicts at all.
 #pragma once
 #include "loa_rules.cuh"
+#include "loa_euler.cuh"
 
 namespace loa {
 
@@ -213,6 +214,29 @@ GAI_HDI bool apply_move_sweep(Side& my, Side& en, int from, int to, const u64* _
 	my.D2 = (my.D2 ^ bit64((int)hd_dp4a(hf, 0x00010000u, 0u))) | t2;
 	en.R &= ~tR; en.C &= ~tC; en.D1 &= ~t1; en.D2 &= ~t2;
 	return cap && (en.R & nbr[to]) == 0;
+}
+
+// apply for the sweep kernel with the Euler characteristics of both colours kept up to date (loa_euler.cuh): the mover's
+// figure loses `from` and gains `to`, the other colour loses `to` on a capture.  Returns true on a capture.
+GAI_HDI bool apply_move_chi(Side& my, Side& en, int& chi_my, int& chi_en, int from, int to, const u64* __restrict__ sqt,
+                            const u64* __restrict__ nbx, const signed char* __restrict__ chitab)
+{
+	const u64 wf = nbx[from], wt = nbx[to];
+	const u32 hf = (u32)(sqt[from] >> 32), ht = (u32)(sqt[to] >> 32);
+	const u64 tR = bit64(to), tC = bit64((int)hd_dp4a(ht, 0x00000001u, 0u)), t1 = bit64((int)hd_dp4a(ht, 0x00000100u, 0u)), t2 = bit64((int)hd_dp4a(ht, 0x00010000u, 0u));
+	const bool cap = (en.R & tR) != 0;
+	const int d_from = chitab[chi_index(my.R, wf)];               // the centre is masked out of its own neighbourhood
+	const u64 r1 = my.R ^ bit64(from);
+	const int d_to = chitab[chi_index(r1, wt)];
+	const int d_cap = chitab[chi_index(en.R, wt)];
+	chi_my += d_to - d_from;
+	chi_en -= cap ? d_cap : 0;
+	my.R = r1 | tR;
+	my.C = (my.C ^ bit64((int)hd_dp4a(hf, 0x00000001u, 0u))) | tC;
+	my.D1 = (my.D1 ^ bit64((int)hd_dp4a(hf, 0x00000100u, 0u))) | t1;
+	my.D2 = (my.D2 ^ bit64((int)hd_dp4a(hf, 0x00010000u, 0u))) | t2;
+	en.R &= ~tR; en.C &= ~tC; en.D1 &= ~t1; en.D2 &= ~t2;
+	return cap;
 }
 
 } // namespace loa

@@ -11,15 +11,19 @@ namespace loa {
 __constant__ DiagTables c_diag2 = make_diag_tables();
 __constant__ SquareTable c_sqt = make_square_table();
 __constant__ LineTable c_lines = make_line_table();
+__constant__ NbxTable c_nbx = make_nbx_table();
+__constant__ ChiTable c_chi = make_chi_table();
 
 struct FastSmem {
 	const uint16_t* lut; const u64* sqt; const u64* lines; const u64* ld; const u64* rd; const u64* nbr; const u32* slt; const u32* tpc;
+	const u64* nbx; const signed char* chi;
 };
 
-// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][4 x 64 x u64 line masks: row, column, ld, rd][64 x u64 neighbourhoods][tail]
+// dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][4 x 64 x u64 line masks: row, column, ld, rd][64 x u64 neighbourhoods]
+//                        [64 x u64 window controls (loa_euler.cuh)][384 B chi deltas][tail]
 //   tail of the static-sweep kernels : [256 x 32 lanes x u32 short-line table][256 x 32 x u32 field-count table]
 //   tail of the per-piece kernels    : [16 x 1024 bytes piece squares]
-constexpr int FAST_SQ_OFF = LUT_BYTES + 6 * 64 * 8;
+constexpr int FAST_SQ_OFF = LUT_BYTES + 7 * 64 * 8 + CHI_TAB_SIZE;
 constexpr int FAST_SMEM_BYTES = FAST_SQ_OFF + 16 * 1024;
 constexpr int SWEEP_SMEM_BYTES = FAST_SQ_OFF + 2 * 256 * 32 * 4;
 
@@ -33,8 +37,12 @@ __device__ __forceinline__ FastSmem load_fast_smem(unsigned char* smem, const ui
 	for (int i = threadIdx.x; i < 64; i += blockDim.x) {
 		sq[i] = c_sqt.w[i]; sq[320 + i] = c_lines.nbr[i];
 		sq[64 + i] = c_lines.line[0][i]; sq[128 + i] = c_lines.line[1][i]; sq[192 + i] = c_lines.line[2][i]; sq[256 + i] = c_lines.line[3][i];
+		sq[384 + i] = c_nbx.w[i];
 	}
+	signed char* chi = reinterpret_cast<signed char*>(sq + 448);
+	for (int i = threadIdx.x; i < CHI_TAB_SIZE; i += blockDim.x) chi[i] = c_chi.d[i];
 	FastSmem f; f.lut = reinterpret_cast<const uint16_t*>(smem); f.sqt = sq; f.lines = sq + 64; f.ld = sq + 192; f.rd = sq + 256; f.nbr = sq + 320;
+	f.nbx = sq + 384; f.chi = chi;
 	f.slt = f.tpc = nullptr;
 	if (SWEEP_TABLES) {
 		u32* t = reinterpret_cast<u32*>(smem + FAST_SQ_OFF);
@@ -50,6 +58,7 @@ struct FastSim {
 	Side my, en;       // side to move / side that just moved
 	u32 side, ply, rq;
 	bool chk_en, chk_my;
+	int chi_my, chi_en; // Euler characteristics of the two figures (static-sweep kernel; loa_euler.cuh)
 };
 
 __device__ __forceinline__ void fsim_init(FastSim& s, u64 white, u64 black, u32 side, const FastSmem& f)
@@ -59,6 +68,7 @@ __device__ __forceinline__ void fsim_init(FastSim& s, u64 white, u64 black, u32 
 	s.en = make_side(s.side ? white : black, f.sqt);
 	s.ply = 0; s.rq = 0xffffffffu;
 	s.chk_en = true; s.chk_my = true;
+	s.chi_my = s.chi_en = 0;
 }
 
 // one ply; -1 while the playout continues, else the outcome code (same semantics as loa_sim.cuh sim_step)
@@ -182,40 +192,59 @@ __device__ __forceinline__ int wstep(FastSim& s, bool alive, gai::Philox4& rnd, 
 	return result;
 }
 
+// The flood fill alone (no pre-filters): only lanes whose Euler characteristic is at most 1 get here -- one group (the game
+// is over), or, rarely, k groups and at least k - 1 holes, or an empty board.
+__device__ __forceinline__ bool wfill(u64 b, bool want)
+{
+	bool res = false;
+	bool pend = want && b != 0;
+	u64 g = b & (0 - b);
+	while (__any_sync(FULL, pend)) {
+		if (pend) {
+			const u64 n = dilate8(g) & b;
+			if (n == g) { pend = false; res = (g == b); }
+			g = n;
+		}
+	}
+	return res;
+}
+
 // One ply of the static-sweep formulation with FIXED register roles: `my` moves, `en` is the side that just moved, and
 // the caller alternates the two argument orders ply by ply instead of swapping sixteen registers (the swap was 32
 // IMAD.MOV per ply).  `phase` = loop iteration & 3: lanes start playouts only on iterations that are multiples of four,
 // so ply & 3 == phase in every lane and the Philox block (4 choice words) is refreshed by ALL lanes in the same iteration
 // (ncu on a per-lane refresh: the 60-instruction Philox block issued in 97 % of warp-plies at 8 active lanes).
-__device__ __forceinline__ int wstep_sweep(Side& my, Side& en, FastSim& s, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies,
+// Connectivity: chi (components - holes) of both colours is carried along and updated by apply_move_chi; the flood fill
+// runs only for a colour whose figure changed in the previous ply AND has chi == 1.
+__device__ __forceinline__ int wstep_sweep(Side& my, Side& en, int& chi_my, int& chi_en, u32& ply, u32 side0, bool alive, gai::Philox4& rnd, u64 key, u64 id, u32 max_plies,
                                            const FastSmem& f, const SweepTabs& lut, u32 phase)
 {
-	const bool c_en = wconnected(en.R, alive && s.chk_en);
+	// one group means chi = 1 - holes <= 1, so chi > 1 proves "not connected" without a fill.  A figure that did not change
+	// since it was last found disconnected keeps its chi: the only repeated fills are those of the rare figures with as many
+	// holes as extra groups.
+	const bool t_en = alive && chi_en <= 1, t_my = alive && chi_my <= 1;
+	const bool c_en = wfill(en.R, t_en);
 	bool c_my = false;
-	if (__any_sync(FULL, alive && s.chk_my)) c_my = wconnected(my.R, alive && s.chk_my);
+	if (__any_sync(FULL, t_my)) c_my = wfill(my.R, t_my);
 	const bool term = c_en | c_my;
-	const bool capped = alive && !term && s.ply >= max_plies;
+	const bool capped = alive && !term && ply >= max_plies;
 	const bool play = alive && !term && !capped;
 	int result = -1;
-	if (term) { const bool wc = s.side ? c_en : c_my, bc = s.side ? c_my : c_en; result = outcome_of(wc, bc); }
+	if (term) { const u32 side = side0 ^ (ply & 1u); const bool wc = side ? c_en : c_my, bc = side ? c_my : c_en; result = outcome_of(wc, bc); }
 	if (capped) result = OUT_CAPPED;
 
 	const RowCounts rc = sweep_rows(my, en, lut);
 	const u32 n = play ? rc.n : 0u;
-	const bool act = n != 0;
-	if (phase == 0) rnd = gai::choice_block(key, id, s.ply >> 2);      // warp-uniform branch
+	if (phase == 0) rnd = gai::choice_block(key, id, ply >> 2);      // warp-uniform branch
 	const u32 idx = gai::choice_index(pick_word(rnd, phase), n);
 	int from, dir;
 	sweep_select(rc, idx, lut, &from, &dir);
 	if (play) {
-		bool cap = false;
-		if (act) {
+		if (n != 0) {
 			const int to = move_target_tab(my.R | en.R, from, dir, f.lines);
-			cap = apply_move_sweep(my, en, from, to, f.sqt, f.nbr);       // true only if the victim was a group of its own
+			apply_move_chi(my, en, chi_my, chi_en, from, to, f.sqt, f.nbx, f.chi);
 		}
-		s.side ^= 1u;
-		s.ply += 1;
-		s.chk_en = act; s.chk_my = cap;
+		ply += 1;
 	}
 	return result;
 }
@@ -230,7 +259,7 @@ __device__ __forceinline__ int wstep_sweep(Side& my, Side& en, FastSim& s, bool 
 // the GPU is refilled from the same piece-count bucket and older playouts have aged towards it.  The order changes which
 // lane runs a playout, never its result (playout id = leaf index * ppl + j).
 __global__ void k_prepare_leaves(const ulonglong2* __restrict__ boards, u32 n, ulonglong2* __restrict__ prep,
-                                 uint8_t* __restrict__ pcount, u32* __restrict__ hist)
+                                 uint8_t* __restrict__ pcount, u32* __restrict__ hist, uint16_t* __restrict__ chi)
 {
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -246,6 +275,9 @@ __global__ void k_prepare_leaves(const ulonglong2* __restrict__ boards, u32 n, u
 	prep[4 * (size_t)i + 1] = make_ulonglong2(w.D1, w.D2);
 	prep[4 * (size_t)i + 2] = make_ulonglong2(b.R, b.C);
 	prep[4 * (size_t)i + 3] = make_ulonglong2(b.D1, b.D2);
+	// Euler characteristic of both figures (low byte white, high byte black, two's complement)
+	const int cw = chi_of(bd.x, c_nbx.w, c_chi.d), cb = chi_of(bd.y, c_nbx.w, c_chi.d);
+	chi[i] = (uint16_t)((u32)(cw & 0xff) | ((u32)(cb & 0xff) << 8));
 }
 
 // hist[0..31] = leaves per piece count, hist[32..63] = scatter cursors (zeroed by the host before k_prepare_leaves)
@@ -259,14 +291,15 @@ __global__ void k_order_leaves(const uint8_t* __restrict__ pcount, u32 n, u32* _
 	order[off + atomicAdd(hist + 32 + pc, 1u)] = i;
 }
 
-template <bool SWEEP, int MAXT, int UNROLL>
+// Per-piece formulation (rules impl 1): persistent, one playout per lane, refill from a global work counter.
+template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm, const u32* __restrict__ order,
                u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
                u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const FastSmem f = load_fast_smem<SWEEP>(smem, g_lut);
+	const FastSmem f = load_fast_smem<false>(smem, g_lut);
 
 	const u64 total = (u64)n_leaves * ppl;
 	const bool ppl_pow2 = (ppl & (ppl - 1u)) == 0;
@@ -276,13 +309,11 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 	u64 item = 0, pid = 0; u32 leaf = 0;
 	bool need = true, exhausted = false;
 	u64 my_plies = 0, my_playouts = 0;
-	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false;
+	s.my = Side{0, 0, 0, 0}; s.en = Side{0, 0, 0, 0}; s.side = 0; s.ply = 0; s.rq = 0; s.chk_en = s.chk_my = false; s.chi_my = s.chi_en = 0;
 	rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
-
-	const SweepTabs lut = sweep_tabs(f.lut, f.slt, f.tpc, lane);
-	for (u32 it = 0;; it += (SWEEP ? (u32)UNROLL : 1u)) {
+	for (;;) {
 		// refill: lanes whose playout ended pull the next (leaf, playout) item; one atomic per warp per refill round
-		const unsigned needmask = (!SWEEP || (it & 3u) == 0) ? __ballot_sync(FULL, need && !exhausted) : 0u;
+		const unsigned needmask = __ballot_sync(FULL, need && !exhausted);
 		if (needmask) {
 			const int leader = __ffs(needmask) - 1;
 			unsigned long long base = 0;
@@ -292,11 +323,11 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 				item = base + __popc(needmask & ((1u << lane) - 1u));
 				if (item >= total) exhausted = true;
 				else {
-					const u32 slot = ppl_pow2 ? (u32)(item >> ppl_shift) : (u32)(item / ppl);      // warp-uniform: no division for 2^k playouts per leaf
+					const u32 slot = ppl_pow2 ? (u32)(item >> ppl_shift) : (u32)(item / ppl);
 					leaf = __ldg(order + slot);
 					pid = first_id + (u64)leaf * ppl + (item - (u64)slot * ppl);       // identity = (leaf, playout), not the schedule
 					const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
-					const ulonglong2* lp = prep + 4 * (size_t)leaf;       // four 16-byte loads per playout: {white R C, white D1 D2, black R C, black D1 D2}
+					const ulonglong2* lp = prep + 4 * (size_t)leaf;
 					const ulonglong2 m0 = __ldg(lp + 2 * side), m1 = __ldg(lp + 2 * side + 1), e0 = __ldg(lp + 2 * (side ^ 1u)), e1 = __ldg(lp + 2 * (side ^ 1u) + 1);
 					s.side = side; s.my = Side{m0.x, m0.y, m1.x, m1.y}; s.en = Side{e0.x, e0.y, e1.x, e1.y};
 					s.ply = 0; s.rq = 0xffffffffu; s.chk_en = true; s.chk_my = true;
@@ -305,31 +336,11 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 			}
 		}
 		if (__all_sync(FULL, exhausted)) break;
-		if constexpr (SWEEP) {
-			// UNROLL plies per trip; the two sides trade places by argument order (UNROLL is even or 1)
-#pragma unroll
-			for (int j = 0; j < UNROLL; ++j) {
-				const u32 phase = UNROLL == 4 ? (u32)j : ((it + (u32)j) & 3u);
-				int o;
-				if (UNROLL == 1) {
-					o = wstep_sweep(s.my, s.en, s, !exhausted && !need, rnd, key, pid, max_plies, f, lut, phase);
-					const Side t = s.my; s.my = s.en; s.en = t;
-				}
-				else if (j & 1) o = wstep_sweep(s.en, s.my, s, !exhausted && !need, rnd, key, pid, max_plies, f, lut, phase);
-				else o = wstep_sweep(s.my, s.en, s, !exhausted && !need, rnd, key, pid, max_plies, f, lut, phase);
-				if (o >= 0) {
-					atomicAdd(out + 4 * (size_t)leaf + o, 1u);
-					my_plies += s.ply; my_playouts += 1;
-					need = true;
-				}
-			}
-		} else {
-			const int o = wstep(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
-			if (o >= 0) {
-				atomicAdd(out + 4 * (size_t)leaf + o, 1u);
-				my_plies += s.ply; my_playouts += 1;
-				need = true;
-			}
+		const int o = wstep(s, !exhausted && !need, rnd, key, pid, max_plies, f, smem + FAST_SQ_OFF);
+		if (o >= 0) {
+			atomicAdd(out + 4 * (size_t)leaf + o, 1u);
+			my_plies += s.ply; my_playouts += 1;
+			need = true;
 		}
 	}
 #pragma unroll
@@ -338,6 +349,95 @@ k_rollout_fast(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ p
 		my_playouts += __shfl_xor_sync(FULL, my_playouts, d);
 	}
 	if (lane == 0) { atomicAdd((unsigned long long*)stats, my_playouts); atomicAdd((unsigned long long*)stats + 1, my_plies); }
+}
+
+// The static-sweep rollout kernel (rules impl 2, the default): one persistent CTA per SM, one playout per lane.
+// Per-lane state that lives across plies is kept to the minimum the 72-register budget of 896 threads allows: the two
+// colours' rotations (16 registers, FIXED roles A = side to move at the leaf, B = the other; the step alternates the
+// argument order), chi of both, the Philox block, the playout id, leaf | side-at-the-leaf << 31, the ply and two 32-bit
+// per-lane counters (a lane plays ~1e4 plies per launch; they are widened when the warp reduces them at the end).
+template <int MAXT, int UNROLL>
+__global__ void __launch_bounds__(MAXT, 1)
+k_rollout_sweep(const uint4* __restrict__ g_lut, const ulonglong2* __restrict__ prep, const u32* __restrict__ stm, const u32* __restrict__ order,
+                const uint16_t* __restrict__ chi16, u32 n_leaves, u32 ppl, u32 max_plies, u64 key, u64 first_id, u32* __restrict__ out,
+                u64* __restrict__ stats, unsigned long long* __restrict__ work_counter)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem<true>(smem, g_lut);
+
+	const u64 total = (u64)n_leaves * ppl;
+	const bool ppl_pow2 = (ppl & (ppl - 1u)) == 0;
+	const u32 ppl_shift = (u32)__ffs((int)ppl) - 1u;
+	const u32 lane = threadIdx.x & 31u;
+	Side A{0, 0, 0, 0}, B{0, 0, 0, 0};
+	int chiA = 0, chiB = 0;
+	gai::Philox4 rnd; rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
+	u64 pid = 0; u32 leafside = 0, ply = 0;
+	bool need = true, exhausted = false;
+	u32 my_plies = 0, my_playouts = 0;
+
+	const SweepTabs lut = sweep_tabs(f.lut, f.slt, f.tpc, lane);
+	for (u32 it = 0;; it += (u32)UNROLL) {
+		// refill (iterations that are multiples of four only, see wstep_sweep): lanes whose playout ended pull the next
+		// (leaf, playout) item; one atomic per warp per refill round
+		const unsigned needmask = (it & 3u) == 0 ? __ballot_sync(FULL, need && !exhausted) : 0u;
+		if (needmask) {
+			const int leader = __ffs(needmask) - 1;
+			unsigned long long base = 0;
+			if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(needmask));
+			base = __shfl_sync(FULL, base, leader);
+			if (need && !exhausted) {
+				const u64 item = base + __popc(needmask & ((1u << lane) - 1u));
+				if (item >= total) exhausted = true;
+				else {
+					const u32 slot = ppl_pow2 ? (u32)(item >> ppl_shift) : (u32)(item / ppl);      // warp-uniform: no division for 2^k playouts per leaf
+					const u32 leaf = __ldg(order + slot);
+					pid = first_id + (u64)leaf * ppl + (item - (u64)slot * ppl);       // identity = (leaf, playout), not the schedule
+					const u32 side = (__ldg(stm + (leaf >> 5)) >> (leaf & 31u)) & 1u;
+					const ulonglong2* lp = prep + 4 * (size_t)leaf;       // four 16-byte loads per playout: {white R C, white D1 D2, black R C, black D1 D2}
+					const ulonglong2 m0 = __ldg(lp + 2 * side), m1 = __ldg(lp + 2 * side + 1), e0 = __ldg(lp + 2 * (side ^ 1u)), e1 = __ldg(lp + 2 * (side ^ 1u) + 1);
+					A = Side{m0.x, m0.y, m1.x, m1.y}; B = Side{e0.x, e0.y, e1.x, e1.y};
+					const u32 ch = __ldg(chi16 + leaf);
+					const int cw = (int)(signed char)(ch & 0xffu), cb = (int)(signed char)(ch >> 8);
+					chiA = side ? cb : cw; chiB = side ? cw : cb;
+					leafside = leaf | (side << 31); ply = 0;
+					need = false;
+				}
+			}
+		}
+		if (__all_sync(FULL, exhausted)) break;
+		// UNROLL plies per trip; with an even UNROLL the two sides trade places by argument order, with UNROLL = 1 by a swap
+#pragma unroll
+		for (int j = 0; j < UNROLL; ++j) {
+			const u32 phase = UNROLL == 4 ? (u32)j : ((it + (u32)j) & 3u);
+			const bool alive = !exhausted && !need;
+			int o;
+			if (UNROLL == 1) {
+				o = wstep_sweep(A, B, chiA, chiB, ply, leafside >> 31, alive, rnd, key, pid, max_plies, f, lut, phase);
+				const Side t = A; A = B; B = t;
+				const int tc = chiA; chiA = chiB; chiB = tc;
+			}
+			else if (j & 1) o = wstep_sweep(B, A, chiB, chiA, ply, leafside >> 31, alive, rnd, key, pid, max_plies, f, lut, phase);
+			else o = wstep_sweep(A, B, chiA, chiB, ply, leafside >> 31, alive, rnd, key, pid, max_plies, f, lut, phase);
+			// per-leaf results: lanes of this warp that finished a playout of the SAME leaf with the SAME outcome in this ply
+			// are reduced first (match-any), one atomic per group
+			const unsigned fin = __ballot_sync(FULL, o >= 0);
+			if (o >= 0) {
+				const u32 leaf = leafside & 0x7fffffffu;
+				const unsigned grp = __match_any_sync(fin, (leaf << 2) | (u32)o);
+				if (lane == (u32)__ffs((int)grp) - 1u) atomicAdd(out + 4 * (size_t)leaf + o, (u32)__popc(grp));
+				my_plies += ply; my_playouts += 1;
+				need = true;
+			}
+		}
+	}
+	u64 wp = my_plies, wq = my_playouts;
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		wp += __shfl_xor_sync(FULL, wp, d);
+		wq += __shfl_xor_sync(FULL, wq, d);
+	}
+	if (lane == 0) { atomicAdd((unsigned long long*)stats, wq); atomicAdd((unsigned long long*)stats + 1, wp); }
 }
 
 // tier-1 sweep through the SAME movegen the rollout kernel uses (persistent grid-stride, one CTA per SM)
@@ -445,6 +545,44 @@ k_playout_trace_fast(const uint4* __restrict__ g_lut, const u64* __restrict__ st
 	}
 }
 
+// Single playouts with full detail THROUGH THE STATIC-SWEEP STEP (wstep_sweep: sweep + select + apply_move_chi + the
+// chi-gated flood fill), one playout per lane, whole warps in lock step until every lane has finished: the tier-2 trace of
+// the default kernel is the default kernel's own code path, final position included.
+__global__ void __launch_bounds__(256, 1)
+k_playout_trace_sweep(const uint4* __restrict__ g_lut, const u64* __restrict__ states, u32 n, u32 max_plies, u64 key, u64 first_id,
+                      uint8_t* __restrict__ outcome, u32* __restrict__ plies, u64* __restrict__ final_states)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const FastSmem f = load_fast_smem<true>(smem, g_lut);
+	const SweepTabs lut = sweep_tabs(f.lut, f.slt, f.tpc, threadIdx.x & 31u);
+	const u32 stride = gridDim.x * blockDim.x;
+	for (u32 base = blockIdx.x * blockDim.x; base < n; base += stride) {
+		const u32 i = base + threadIdx.x;
+		bool alive = i < n;
+		gai::Philox4 rnd;
+		rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
+		Side A{0, 0, 0, 0}, B{0, 0, 0, 0};
+		int chiA = 0, chiB = 0; u32 ply = 0, side0 = 0;
+		if (alive) {
+			const u64 w = states[3 * (size_t)i], b = states[3 * (size_t)i + 1];
+			side0 = (u32)states[3 * (size_t)i + 2] & 1u;
+			A = make_side(side0 ? b : w, f.sqt); B = make_side(side0 ? w : b, f.sqt);
+			chiA = chi_of(A.R, f.nbx, f.chi); chiB = chi_of(B.R, f.nbx, f.chi);
+		}
+		for (u32 it = 0; __any_sync(FULL, alive); ++it) {
+			const int o = (it & 1u) ? wstep_sweep(B, A, chiB, chiA, ply, side0, alive, rnd, key, first_id + i, max_plies, f, lut, it & 3u)
+			                        : wstep_sweep(A, B, chiA, chiB, ply, side0, alive, rnd, key, first_id + i, max_plies, f, lut, it & 3u);
+			if (alive && o >= 0) {
+				outcome[i] = (uint8_t)o; plies[i] = ply;
+				final_states[3 * (size_t)i] = side0 ? B.R : A.R;              // A = the colour that was to move at the start
+				final_states[3 * (size_t)i + 1] = side0 ? A.R : B.R;
+				final_states[3 * (size_t)i + 2] = side0 ^ (ply & 1u);
+				alive = false;
+			}
+		}
+	}
+}
+
 } // namespace loa
 
 using namespace loa;
@@ -461,25 +599,26 @@ void loa_fast_build_lut_host(uint16_t* lut)
 cudaError_t loa_fast_prepare()
 {
 	cudaError_t e;
-	if ((e = cudaFuncSetAttribute(k_rollout_fast<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
-#define GAI_PREP(T, U) if ((e = cudaFuncSetAttribute(k_rollout_fast<true, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_rollout_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
+#define GAI_PREP(T, U) if ((e = cudaFuncSetAttribute(k_rollout_sweep<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
 	GAI_PREP(1024, 1) GAI_PREP(768, 1) GAI_PREP(512, 1) GAI_PREP(1024, 2) GAI_PREP(896, 2) GAI_PREP(768, 2) GAI_PREP(640, 2) GAI_PREP(512, 2) GAI_PREP(1024, 4) GAI_PREP(768, 4) GAI_PREP(512, 4)
 #undef GAI_PREP
 	if ((e = cudaFuncSetAttribute(k_movegen_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(k_playout_trace_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_movegen_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(k_successor_hash_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES)) != cudaSuccess) return e;
 	return cudaFuncSetAttribute(k_playout_trace_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
 }
 static int fast_grid(uint32_t n, int threads, int sms) { const int need = (int)((n + threads - 1) / threads); return need < sms ? (need ? need : 1) : sms; }
 
-void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, uint8_t* d_pcount, uint32_t* d_hist, uint32_t* d_order, cudaStream_t st)
+void launch_loa_prepare_leaves(const void* d_boards, uint32_t n, void* d_prep, uint8_t* d_pcount, uint32_t* d_hist, uint32_t* d_order, uint16_t* d_chi, cudaStream_t st)
 {
 	if (!n) return;
-	k_prepare_leaves<<<(n + 127) / 128, 128, 0, st>>>((const ulonglong2*)d_boards, n, (ulonglong2*)d_prep, d_pcount, d_hist);
+	k_prepare_leaves<<<(n + 127) / 128, 128, 0, st>>>((const ulonglong2*)d_boards, n, (ulonglong2*)d_prep, d_pcount, d_hist, d_chi);
 	k_order_leaves<<<(n + 255) / 256, 256, 0, st>>>(d_pcount, n, d_hist, d_order);
 }
 
-void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, const uint32_t* d_order, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
+void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint32_t* d_stm, const uint32_t* d_order, const uint16_t* d_chi, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies,
                              uint64_t key, uint64_t first_id, uint32_t* d_out, uint64_t* d_stats, unsigned long long* d_counter,
                              int threads, int sms, int sweep, cudaStream_t st)
 {
@@ -493,17 +632,19 @@ void launch_loa_rollout_fast(const void* d_lut, const void* d_boards, const uint
 		if (t < threads) threads = t;
 	}
 	const int blocks = fast_grid(total > 0xffffffffull ? 0xffffffffu : (uint32_t)total, threads, sms);
-#define GAI_RL_ARGS (const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, d_out, (u64*)d_stats, d_counter
+#define GAI_RL_ARGS (const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, d_chi, n_leaves, ppl, max_plies, key, first_id, d_out, (u64*)d_stats, d_counter
+#define GAI_RF_ARGS (const uint4*)d_lut, (const ulonglong2*)d_boards, d_stm, d_order, n_leaves, ppl, max_plies, key, first_id, d_out, (u64*)d_stats, d_counter
 	// sweep: 0 = per-piece formulation, else the unroll factor of the static-sweep kernel (1, 2 or 4 plies per loop trip)
-#define GAI_RL(T, U) k_rollout_fast<true, T, U><<<blocks, threads, SWEEP_SMEM_BYTES, st>>>(GAI_RL_ARGS)
+#define GAI_RL(T, U) k_rollout_sweep<T, U><<<blocks, threads, SWEEP_SMEM_BYTES, st>>>(GAI_RL_ARGS)
 #define GAI_RL_T(U) do { if (threads > 768) GAI_RL(1024, U); else if (threads > 512) GAI_RL(768, U); else GAI_RL(512, U); } while (0)
-	if (!sweep) k_rollout_fast<false, 1024, 1><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RL_ARGS);
+	if (!sweep) k_rollout_fast<1024><<<blocks, threads, FAST_SMEM_BYTES, st>>>(GAI_RF_ARGS);
 	else if (sweep >= 4) GAI_RL_T(4);
 	else if (sweep >= 2) { if (threads > 896) GAI_RL(1024, 2); else if (threads > 768) GAI_RL(896, 2); else if (threads > 640) GAI_RL(768, 2); else if (threads > 512) GAI_RL(640, 2); else GAI_RL(512, 2); }
 	else GAI_RL_T(1);
 #undef GAI_RL_T
 #undef GAI_RL
 #undef GAI_RL_ARGS
+#undef GAI_RF_ARGS
 }
 void launch_loa_movegen_sweep(const void* d_lut, const void* d_states, uint32_t n, uint8_t* d_counts, uint8_t* d_moves, int sms, cudaStream_t st)
 { if (n) k_movegen_sweep<<<fast_grid(n, 256, sms), 256, SWEEP_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, d_counts, d_moves); }
@@ -514,3 +655,6 @@ void launch_loa_successor_hash_fast(const void* d_lut, const void* d_states, uin
 void launch_loa_playout_trace_fast(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
                                    uint8_t* d_outcome, uint32_t* d_plies, void* d_final, int sms, cudaStream_t st)
 { if (n) k_playout_trace_fast<<<fast_grid(n, 256, sms), 256, FAST_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, max_plies, key, first_id, d_outcome, d_plies, (u64*)d_final); }
+void launch_loa_playout_trace_sweep(const void* d_lut, const void* d_states, uint32_t n, uint32_t max_plies, uint64_t key, uint64_t first_id,
+                                    uint8_t* d_outcome, uint32_t* d_plies, void* d_final, int sms, cudaStream_t st)
+{ if (n) k_playout_trace_sweep<<<fast_grid(n, 256, sms), 256, SWEEP_SMEM_BYTES, st>>>((const uint4*)d_lut, (const u64*)d_states, n, max_plies, key, first_id, d_outcome, d_plies, (u64*)d_final); }

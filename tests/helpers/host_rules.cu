@@ -63,6 +63,10 @@ static loa::SweepTabs host_tabs()
 static const loa::SquareTable g_sqt = loa::make_square_table();
 static const loa::DiagTables g_diag = loa::make_diag_tables();
 static const loa::LineTable g_lines = loa::make_line_table();
+static const loa::NbxTable g_nbx = loa::make_nbx_table();
+static const loa::ChiTable g_chi = loa::make_chi_table();
+// Euler characteristic (components - holes) of a board by the product's table-driven code
+int host_loa_chi(uint64_t b) { return loa::chi_of(b, g_nbx.w, g_chi.d); }
 void host_loa_sweep_movegen_batch(const uint64_t* states, unsigned n, uint8_t* counts, uint8_t* moves)
 {
 	const loa::SweepTabs lut = host_tabs();
@@ -88,23 +92,26 @@ void host_loa_sweep_playout_batch(const uint64_t* states, unsigned n, unsigned m
 		loa::Side my = loa::make_side(side ? states[3 * i + 1] : states[3 * i], g_sqt.w), en = loa::make_side(side ? states[3 * i] : states[3 * i + 1], g_sqt.w);
 		unsigned ply = 0; int out = -1;
 		gai::Philox4 rnd{};
-		bool chk_en = true, chk_my = true;
+		int chi_my = loa::chi_of(my.R, g_nbx.w, g_chi.d), chi_en = loa::chi_of(en.R, g_nbx.w, g_chi.d);
 		for (;;) {
-			const bool c_en = chk_en && loa::connected_fast(en.R), c_my = chk_my && loa::connected_fast(my.R);
+			// the kernel's test (wstep_sweep): the flood fill only for a colour whose chi is at most 1
+			const bool c_en = chi_en <= 1 && loa::connected(en.R), c_my = chi_my <= 1 && loa::connected(my.R);
 			if (c_en | c_my) { out = loa::outcome_of(side ? c_en : c_my, side ? c_my : c_en); break; }
 			if (ply >= max_plies) { out = loa::OUT_CAPPED; break; }
 			const loa::RowCounts rc = loa::sweep_rows(my, en, lut);
+			if ((ply & 3u) == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
 			if (rc.n) {
-				if ((ply & 3u) == 0 || ply == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2);
 				const unsigned idx = gai::choice_index(rnd.v[ply & 3u], rc.n);
 				int from, dir;
 				loa::sweep_select(rc, idx, lut, &from, &dir);
 				const int to = loa::move_target_tab(my.R | en.R, from, dir, &g_lines.line[0][0]);
 				if (to != loa::move_target(my.R | en.R, from, dir, g_diag.ld, g_diag.rd)) { out = 0xee; break; }
-				chk_my = loa::apply_move_sweep(my, en, from, to, g_sqt.w, g_lines.nbr);
-				chk_en = true;
-			} else { chk_en = false; chk_my = false; if ((ply & 3u) == 0) rnd = gai::choice_block(key, first_id + i, ply >> 2); }
+				loa::apply_move_chi(my, en, chi_my, chi_en, from, to, g_sqt.w, g_nbx.w, g_chi.d);
+				// the incrementally maintained chi must equal a recount from scratch
+				if (chi_my != loa::chi_of(my.R, g_nbx.w, g_chi.d) || chi_en != loa::chi_of(en.R, g_nbx.w, g_chi.d)) { out = 0xed; break; }
+			}
 			const loa::Side t = my; my = en; en = t;
+			const int tc = chi_my; chi_my = chi_en; chi_en = tc;
 			side ^= 1u; ++ply;
 		}
 		outcome[i] = (uint8_t)out; plies[i] = ply;

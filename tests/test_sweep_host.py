@@ -59,3 +59,57 @@ def test_small_tables_by_definition(hostlib):
                 up_short = (short >> (2 * p + 1)) & 1
                 assert up_short == (up_full if p + n < 4 else 0)
                 assert ((short >> (2 * p)) & 1) == ((full >> (2 * p)) & 1)
+
+
+def _components_and_holes(b):
+    """8-connected components of the set squares and holes = 4-connected regions of empty squares that do not reach the
+    border (brute force, by definition)."""
+    cells = {(i // 8, i % 8) for i in range(64) if (b >> i) & 1}
+    seen, comps = set(), 0
+    for c in cells:
+        if c in seen:
+            continue
+        comps += 1
+        st = [c]; seen.add(c)
+        while st:
+            r, k = st.pop()
+            for dr in (-1, 0, 1):
+                for dc in (-1, 0, 1):
+                    n = (r + dr, k + dc)
+                    if n in cells and n not in seen:
+                        seen.add(n); st.append(n)
+    # background on a 10 x 10 frame: everything 4-connected to the frame is "outside"
+    empty = {(r, k) for r in range(-1, 9) for k in range(-1, 9)} - cells
+    seen, regions = set(), 0
+    for c in empty:
+        if c in seen:
+            continue
+        regions += 1
+        st = [c]; seen.add(c)
+        while st:
+            r, k = st.pop()
+            for n in ((r + 1, k), (r - 1, k), (r, k + 1), (r, k - 1)):
+                if n in empty and n not in seen:
+                    seen.add(n); st.append(n)
+    return comps, regions - 1
+
+
+def test_euler_characteristic_is_components_minus_holes(hostlib, oracle):
+    """loa_euler.cuh: chi = components - holes for arbitrary boards (so chi != 1 proves "not one group"), and the
+    component count agrees with the reference's calcNumGroups (LinesOfActionZasady.cpp:271-305)."""
+    hostlib.host_loa_chi.argtypes = [ctypes.c_uint64]
+    hostlib.host_loa_chi.restype = ctypes.c_int
+    rng = np.random.RandomState(5)
+    boards = [0, 1, 0xFFFFFFFFFFFFFFFF, 0x0000001c141c0000, 0x00003c24243c0000, 0x0000001008140800 | 0x8000000000000001, 0x7e0000000000007e, 0x0081818181818100]
+    for dens in (0.1, 0.2, 0.35, 0.5, 0.7):
+        for _ in range(200):
+            boards.append(int(sum(1 << i for i in range(64) if rng.rand() < dens)))
+    S = oracle.gen_uniform(500, 9)
+    boards += [int(x) for x in S[:, 0]] + [int(x) for x in S[:, 1]]
+    holes_seen = 0
+    for b in boards:
+        c, h = _components_and_holes(b)
+        assert hostlib.host_loa_chi(b) == c - h, hex(b)
+        assert oracle.num_groups(b) == c
+        holes_seen += h > 0
+    assert holes_seen > 50
