@@ -647,6 +647,7 @@ int gai_loa_gen_reachable(gai_ctx* ctx, uint32_t n, uint64_t key, uint32_t max_k
 }
 
 // ---- Pan ---------------------------------------------------------------------------------------------
+static inline uint64_t known_hand_count(uint64_t w) { return w & 15; }
 static int pan_check_np(gai_ctx* ctx, int np)
 {
 	if (np < 2 || np > 4) return fail(ctx, GAI_ERR_INVALID, "num_players must be 2, 3 or 4");
@@ -804,13 +805,30 @@ int gai_pan_determinize(const gai_pan_state* known, int np, int player, uint32_t
 	// own hand and stack must be certain (00 / 11)
 	auto crisp = [](uint64_t c) { return (((c >> 1) ^ c) & 0x555555555555ull) == 0; };
 	if (!crisp(stack) || !crisp(own)) return GAI_ERR_INVALID;
-	int unseen[24], nu = 0, need = 0, cnt[4] = { 0, 0, 0, 0 };
-	for (int c = 0; c < 24; ++c) if (!((stack >> (2 * c)) & 3) && !((own >> (2 * c)) & 3)) unseen[nu++] = c;
-	for (int p = 0; p < np; ++p) { cnt[p] = (int)(known->w[1 + p] & 15); if (p != player) need += cnt[p]; }
-	if (need != nu) return GAI_ERR_INVALID;              // (a count field wrapped past 15, or an inconsistent state)
+	// What the view KNOWS about the other hands: after a take the reference's apply_move does hand.cards |= cards
+	// (GraWPanaZasadyV2.cpp:541-545), so those cards are certain (11) in the taker's hand of every player's view; with three
+	// or four players an unseen card is only ever marked 10 / 01 (CreatePlayerKnownState :216-233), so 11 in another hand
+	// means "held by that player".  (Two players: the view is complete, every unseen card is the opponent's, marked 11.)
+	int unseen[24], nu = 0, cnt[4] = { 0, 0, 0, 0 }, need[4] = { 0, 0, 0, 0 };
+	uint64_t held[4] = { 0, 0, 0, 0 };
+	for (int p = 0; p < np; ++p) cnt[p] = (int)(known_hand_count(known->w[1 + p]));
+	int total_need = 0;
+	for (int c = 0; c < 24; ++c) {
+		if (((stack >> (2 * c)) & 3) || ((own >> (2 * c)) & 3)) continue;
+		int holder = -1;
+		if (np >= 3) for (int p = 0; p < np; ++p) if (p != player && (((known->w[1 + p] >> 4) >> (2 * c)) & 3) == 3) { holder = p; break; }
+		if (holder >= 0) held[holder] |= 3ull << (2 * c); else unseen[nu++] = c;
+	}
+	for (int p = 0; p < np; ++p) {
+		if (p == player) continue;
+		need[p] = cnt[p] - __builtin_popcountll(held[p]) / 2;
+		if (need[p] < 0) return GAI_ERR_INVALID;            // (a count field wrapped past 15, or an inconsistent state)
+		total_need += need[p];
+	}
+	if (total_need != nu) return GAI_ERR_INVALID;
 	// rule constraint: on an empty stack the player to move holds the 9 of hearts (GraWPanaZasadyV2.cpp:127-130,415-418)
 	const int cp = (int)((known->w[0] >> 48) & 7);
-	const bool pin9h = stack == 0 && cp != player && cp < np && nu > 0 && unseen[0] == 0 && cnt[cp] > 0;
+	const bool pin9h = stack == 0 && cp != player && cp < np && nu > 0 && unseen[0] == 0 && need[cp] > 0;
 	for (uint32_t i = 0; i < n_samples; ++i) {
 		int deck[24];
 		for (int k = 0; k < nu; ++k) deck[k] = unseen[k];
@@ -829,7 +847,8 @@ int gai_pan_determinize(const gai_pan_state* known, int np, int player, uint32_t
 			uint64_t cards = 0;
 			if (p == player) cards = own;
 			else {
-				int take = cnt[p];
+				cards = held[p];                           // what the view already knows this player holds
+				int take = need[p];
 				if (pin9h && p == cp) { cards |= 3ull; --take; }
 				for (int k = 0; k < take; ++k) cards |= 3ull << (2 * deck[at++]);
 			}

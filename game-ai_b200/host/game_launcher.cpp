@@ -14,6 +14,9 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <fstream>
 #include <iostream>
 #include <mutex>
@@ -146,8 +149,20 @@ static std::string xml_escape(const std::string& s)
 	return o;
 }
 
+// a crash inside a plugin should say where: print the call stack before dying
+static void crash_handler(int sig)
+{
+	void* frames[64];
+	const int n = backtrace(frames, 64);
+	const char msg[] = "GameLauncher: fatal signal, call stack:\n";
+	if (write(2, msg, sizeof msg - 1) < 0) {}
+	backtrace_symbols_fd(frames, n, 2);
+	signal(sig, SIG_DFL); raise(sig);
+}
+
 int main(int argc, char** argv)
 {
+	signal(SIGSEGV, crash_handler); signal(SIGABRT, crash_handler); signal(SIGFPE, crash_handler);
 	std::string xml = "run_config_loa.xml", plugin_dir, save_file;
 	std::vector<std::string> pnames(4);
 	int num_games = -1, round_limit = -1, verbose = 0, num_threads = -1;

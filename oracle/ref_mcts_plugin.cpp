@@ -6,7 +6,9 @@
 // same controller loop.  The reference player talks to the game only through IGameRules* (GameRules.h:14-50), whose vtable
 // include/gameai/GameRules.h reproduces slot for slot, so it runs on this repo's rules plugin object unchanged.  What differs
 // between the two header sets is the configuration type (boost::property_tree::ptree there, gai::Config here) and the metrics
-// value type; this file converts both.  Nothing in the product loads this library.
+// value type; this file converts both.  Two things are NOT the reference's in this build, both so that whole matches can
+// finish, neither touching the search policy: the pool allocator (shim_plugin/object_pool_multisize.h explains why) and
+// one guard against an empty candidate set in Player::selectMove (oracle/Makefile).  Nothing in the product loads this library.
 #include <map>
 #include <sstream>
 #include <string>

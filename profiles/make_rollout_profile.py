@@ -15,8 +15,8 @@ g = lambda k: float(vals[hdr.index(k)])
 wi = g("smsp__inst_executed.sum")
 lanes = g("smsp__thread_inst_executed_per_inst_executed.ratio")
 d = {
-    "source": "profiles/r01_v15_ncu_summary.txt <- %s (ncu --set full --clock-control none, one launch of %s; %d leaves x %d playouts)" % (
-        os.path.basename(rep), vals[hdr.index("Kernel Name")].split("(")[0], b["config"]["leaves_per_gpu"], b["config"]["playouts_per_leaf"]),
+    "source": "profiles/%s_ncu_summary.txt <- %s (ncu --set full --clock-control none, one launch of %s; %d leaves x %d playouts)" % (
+        tag.replace("-", "_"), os.path.basename(rep), vals[hdr.index("Kernel Name")].split("(")[0], b["config"]["leaves_per_gpu"], b["config"]["playouts_per_leaf"]),
     "tag": tag,
     "leaves_per_launch": b["config"]["leaves_per_gpu"],
     "thread_plies_per_launch": plies_per_launch,

@@ -41,8 +41,9 @@ def main():
                 print("%-90s %s" % (k, d[k]))
         if len(sys.argv) > 2:
             plies = float(sys.argv[2])
-            wi = float(d["smsp__inst_executed.sum"].split()[0]); ti = float(d["smsp__thread_inst_executed.sum"].split()[0])
-            print("warp_inst_per_thread_ply %.2f   thread_inst_per_ply %.1f" % (wi / plies, ti / plies))
+            wi = float(d["smsp__inst_executed.sum"].split()[0])
+            lanes = float(d["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0])
+            print("warp_inst_per_thread_ply %.2f   warp_inst_per_warp_ply_if_full %.1f   thread_inst_per_ply %.1f" % (wi / plies, 32 * wi / plies, wi * lanes / plies))
         print()
 
 

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Tier 3, win rate: the GPU-backed player in its reference-like mode against the reference's own MC::Player (test-only plugin
+oracle/_ref/librefmctsplayer.so) at the same simulation budget, both colours, with reference-vs-reference as the control and both
+against a random mover (aborted-game rates).  MEASUREMENT SCRIPT (test infrastructure: it loads oracle/_ref).
+usage: python profiles/tier3_match.py [games_per_pairing] [sims] [threads] [--fake]   (--fake: CPU box, device replaced by the oracle-backed stub)"""
+import json, os, subprocess, sys, math
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+L = os.path.join(ROOT, "game-ai_b200", "host", "GameLauncher")
+XML = os.path.join(ROOT, "tests", "golden", "run_config_tier3.xml")
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+games = int(args[0]) if len(args) > 0 else 64
+sims = int(args[1]) if len(args) > 1 else 200
+threads = int(args[2]) if len(args) > 2 else (os.cpu_count() or 1)
+env = dict(os.environ)
+if "--fake" in sys.argv:
+    env["LD_PRELOAD"] = os.path.join(ROOT, "tests", "helpers", "libfakegpu.so")
+
+
+def match(p1, p2, seed):
+    r = subprocess.run([L, "--xml", XML, "--plugins", os.path.join(ROOT, "oracle", "_ref"), "--p1", p1, "--p2", p2, "--ng", str(games),
+                        "--threads", str(threads), "--seed", str(seed), "-q"], capture_output=True, text=True, env=env, timeout=7200)
+    assert r.returncode == 0, r.stderr[-1000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    return {"p1": p1, "p2": p2, "games": d["games"], "aborted": d["aborted"], "p1_win": d["players"][0]["win"], "p2_win": d["players"][1]["win"],
+            "p1_pts": d["players"][0]["pts"], "p2_pts": d["players"][1]["pts"], "seconds": d["seconds"]}
+
+
+S = "move_sim_limit=%d" % sims
+out = {"sims_per_move": sims, "games_per_pairing": games, "device": "fake (oracle playouts)" if "--fake" in sys.argv else "gpu", "pairings": []}
+for p1, p2, seed in (("gpu " + S, "ref " + S, 101), ("ref " + S, "gpu " + S, 102), ("ref " + S, "ref " + S + " random_seed=977", 103),
+                     ("gpu " + S, "random", 104), ("ref " + S, "random", 105)):
+    m = match(p1, p2, seed)
+    out["pairings"].append(m)
+    print(json.dumps(m), file=sys.stderr, flush=True)
+P = out["pairings"]
+# score of a side = (wins + half of the draws and aborted games) / games
+def score(wins, other_wins, n): return (wins + 0.5 * (n - wins - other_wins)) / n
+g = score(P[0]["p1_win"] + P[1]["p2_win"], P[0]["p2_win"] + P[1]["p1_win"], 2 * games)
+c = score(P[2]["p1_win"], P[2]["p2_win"], games)
+out["gpu_vs_ref_score"] = g
+out["gpu_vs_ref_sigma"] = math.sqrt(0.25 / (2 * games))
+out["control_ref_as_white_score"] = c
+out["aborted_rate_vs_random"] = {"gpu": P[3]["aborted"] / games, "ref": P[4]["aborted"] / games}
+out["win_rate_vs_random_of_finished"] = {"gpu": P[3]["p1_win"] / max(1, games - P[3]["aborted"]), "ref": P[4]["p1_win"] / max(1, games - P[4]["aborted"])}
+print(json.dumps(out, indent=1))

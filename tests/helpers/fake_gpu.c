@@ -86,6 +86,16 @@ int gai_wait(gai_ctx* c, int ticket, gai_rollout_stats* st)
 	if (c->bad[s]) { strcpy(c->err, "child count mismatch"); return GAI_ERR_INVALID; }
 	return GAI_OK;
 }
+/* the synchronous host-buffer call (used by the INTEGRATION.md section-2 stub, oracle/ref_mcts_gpu_capi.cpp) */
+int gai_loa_rollout(gai_ctx* c, const gai_loa_state* leaves, uint32_t n, uint32_t ppl, uint32_t max_plies, uint64_t key, uint64_t first_id, gai_loa_result* out, gai_rollout_stats* st)
+{
+	if (st) memset(st, 0, sizeof *st);
+	if (n == 0) return GAI_OK;
+	if (ppl == 0) { strcpy(c->err, "playouts_per_leaf must be >= 1"); return GAI_ERR_INVALID; }
+	play(c, 0, (const uint64_t*)leaves, n, ppl, max_plies, key, first_id, out);
+	if (st) { st->playouts = c->playouts[0]; st->plies = c->plies[0]; st->kernel_ms = st->total_ms = 0.01f; }
+	return GAI_OK;
+}
 int gai_inflight(const gai_ctx* c) { int k = 0; for (int i = 0; i < GAI_MAX_INFLIGHT; ++i) k += c->busy[i]; return k; }
 
 /* single-process stand-ins for the NCCL entry points (world size 1) */

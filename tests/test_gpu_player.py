@@ -24,12 +24,13 @@ def test_gpu_mcts_beats_random_and_shallow_alphabeta():
     # A game the controller aborts (repeated position / round limit, GameController.cpp:59-97) is neither a win nor a
     # loss: with best_move_value_eps 0.05 a side that is winning everywhere picks among near-equal moves at random and
     # can shuffle into a repetition against a random mover, exactly as the reference player does.
-    res = run("--p1", "mcts move_sim_limit=300000 random_seed=21 philox_seed=22", "--p2", "random random_seed=23", "--ng", "4", "--seed", "3")
+    res = run("--p1", "mcts move_sim_limit=1000000 random_seed=21 philox_seed=22", "--p2", "random random_seed=23", "--ng", "4", "--seed", "3")
     assert res["players"][0]["lose"] == 0 and res["players"][0]["win"] >= 2, res
     assert res["players"][0]["win"] + res["aborted"] == res["games"], res
     stats = res["players"][0]["stats"]
     assert float(stats["playouts_per_sec"]) > 1e5 and float(stats["gpu_batches"]) > 0
-    res = run("--p1", "ab3 search_depth=2 random_seed=31", "--p2", "mcts move_sim_limit=300000 random_seed=32 philox_seed=33", "--ng", "3", "--seed", "4")
+    # (batch-by-expansion spends ~1100 playouts per selection: the same tree depth needs a larger playout budget)
+    res = run("--p1", "ab3 search_depth=2 random_seed=31", "--p2", "mcts move_sim_limit=3000000 random_seed=32 philox_seed=33", "--ng", "3", "--seed", "4")
     assert res["players"][1]["lose"] == 0 and res["players"][1]["win"] >= 1, res
 
 

@@ -64,3 +64,44 @@ def test_rejects_inconsistent_views():
         g.pan_determinize(bad, 3, 0, 4)
     with pytest.raises(g.GaiError):
         g.pan_determinize(view, 3, 1, 4)                                              # player 1's own hand is fuzzy in player 0's view
+
+
+def test_cards_an_opponent_was_seen_taking_stay_in_that_hand():
+    """After a take the taker's cards are certain (11) in everybody's view (apply_move, GraWPanaZasadyV2.cpp:541-545, which
+    UpdatePlayerKnownState :313-324 runs on the view): every sampled deal must leave them in the taker's hand."""
+    from oracle import pan
+    po = pan.port()
+    found = 0
+    for npl in (3, 4):
+        S = po.gen_reachable(npl, 400, 77 + npl, 40)
+        for i, full in enumerate(S):
+            c, m = po.movegen_batch(npl, full[None])
+            takes = [int(m[0, k]) for k in range(int(c[0])) if ((int(m[0, k]) >> 51) & 7) == 1]      # Move::take_cards
+            if not takes:
+                continue
+            mover = (int(full[0]) >> 48) & 7
+            observer = (mover + 1) % npl
+            fstack, fhands, fcounts = fields(full)
+            if sum(fcounts[:npl]) + bin(fstack).count("1") // 2 != 24:
+                continue
+            view = po.player_known_state(npl, full, observer)
+            mv = np.array([takes[0]], dtype=np.uint64)
+            view2 = po.apply_batch(npl, view[None], mv)[0]           # what UpdatePlayerKnownState does to the view
+            full2 = po.apply_batch(npl, full[None], mv)[0]
+            taken = takes[0] & M48
+            assert crisp(taken) and taken
+            s2, _, c2 = fields(full2)
+            if sum(c2[:npl]) + bin(s2).count("1") // 2 != 24:
+                continue                                               # the taker's 4-bit count wrapped past 15
+            D = g.pan_determinize(view2, npl, observer, 32, key=5, first_id=i)
+            for d in D:
+                stack, hands, counts = fields(d)
+                assert hands[mover] & taken == taken                  # the seen cards are where they were seen going
+                assert stack == fields(full2)[0] and counts[:npl] == fields(full2)[2][:npl]
+                allc = stack
+                for p in range(npl):
+                    assert crisp(hands[p]) and bin(hands[p]).count("1") == 2 * counts[p] and allc & hands[p] == 0
+                    allc |= hands[p]
+                assert allc == M48
+            found += 1
+    assert found > 20
