@@ -51,7 +51,9 @@ GAI_HDI int hd_ffsll(u64 x)
 GAI_HDI u32 hd_byte_perm(u32 a, u32 b, u32 sel)           // PRMT, default mode (selector nibbles 0-7, no sign replication used here)
 {
 #if defined(__CUDA_ARCH__)
-	return __byte_perm(a, b, sel);
+	u32 r;                                          // prmt.b32 directly: __byte_perm() first masks the selector with 0x7777 (one more LOP3);
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));      // every selector used here has nibbles 0-7 (no sign replication)
+	return r;
 #else
 	const u64 v = (u64)a | ((u64)b << 32);
 	u32 r = 0;

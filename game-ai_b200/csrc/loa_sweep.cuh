@@ -35,6 +35,11 @@ struct WeightTab { u32 w37[4], w2[4], w128[4], w8[4]; };
 __constant__ WeightTab c_wt = { { 37u, 37u << 8, 37u << 16, 37u << 24 }, { 2u, 2u << 8, 2u << 16, 2u << 24 },
                                 { 128u, 128u << 8, 128u << 16, 128u << 24 }, { 8u, 8u << 8, 8u << 16, 8u << 24 } };
 #if defined(__CUDA_ARCH__)
+#define GAI_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define GAI_WARP_ANY(p) (p)
+#endif
+#if defined(__CUDA_ARCH__)
 typedef u32 LutRef;                                   // shared-memory byte address of the line LUT
 typedef u32 TabRef;                                   // shared-memory byte address of a per-lane table, this lane's column
 #define GAI_MADC(x, cname, cval, y) ((x) * cname + (y))
@@ -237,8 +242,13 @@ GAI_HDI RowCounts sweep_rows(const Side& my, const Side& en, const SweepTabs& lu
 	thi = GAI_MADC(tpc_of<1>(lut.tpc, p2), c_two, 2, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p2), c_two, 2, thi);
 	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p4), c_four, 4, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p4), c_four, 4, tlo);
 	thi = GAI_MADC(tpc_of<1>(lut.tpc, p4), c_four, 4, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p4), c_four, 4, thi);
-	tlo = GAI_MADC(tpc_of<0>(lut.tpc, p8), c_eight, 8, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p8), c_eight, 8, tlo);
-	thi = GAI_MADC(tpc_of<1>(lut.tpc, p8), c_eight, 8, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p8), c_eight, 8, thi);
+	// the eights plane is set only where EIGHT or more of the twelve words carry the same (row, sense) flag -- three own
+	// pieces in one row all moving the same way along three line types -- so it is empty in almost every position: the
+	// whole warp skips its four lookups unless some lane needs them (every caller runs this function warp-synchronously)
+	if (GAI_WARP_ANY(p8 != 0)) {
+		tlo = GAI_MADC(tpc_of<0>(lut.tpc, p8), c_eight, 8, tlo); tlo = GAI_MADC(tpc_of<2>(lut.tpc, p8), c_eight, 8, tlo);
+		thi = GAI_MADC(tpc_of<1>(lut.tpc, p8), c_eight, 8, thi); thi = GAI_MADC(tpc_of<3>(lut.tpc, p8), c_eight, 8, thi);
+	}
 	rc.plo = tlo * BM;                                   // byte i = rows 0..i   (n <= 96 < 256: no byte overflows)
 	rc.phi = thi * BM + (rc.plo >> 24) * BM;
 	rc.n = rc.phi >> 24;

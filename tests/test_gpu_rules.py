@@ -48,6 +48,19 @@ def test_committed_reference_corpus_on_gpu(gpu):
     assert (gpu.apply(S, G["mv_last"]) == G["apply_last"]).all()
 
 
+def test_crowded_rows(gpu, oracle):
+    """Four own pieces of one square colour in one row, all free to move the same way: the positions that reach the top
+    plane of the sweep kernel's carry-save row counter (skipped under a warp vote everywhere else)."""
+    from test_sweep_host import crowded_rows
+    S = crowded_rows()
+    c, m = gpu.movegen(S); oc, om = oracle.movegen_batch(S)
+    assert (c == oc).all() and (m == om).all()
+    assert c.max() >= 20
+    counts, st = gpu.rollout(S, 4, 50000, 0xC0FFEE, 0)
+    ocn, opl = oracle.rollout_states(S, 4, 50000, 0xC0FFEE, 0)
+    assert (counts == ocn).all() and st["plies"] == opl
+
+
 def test_empty_and_ragged(gpu, oracle):
     e = np.zeros((0, 3), np.uint64)
     c, m = gpu.movegen(e)

@@ -12,8 +12,21 @@ def corpus(oracle, n, seed):
     return np.ascontiguousarray(np.concatenate([oracle.gen_reachable(n, seed), oracle.gen_uniform(n, seed)]))
 
 
+def crowded_rows():
+    """Positions where one row holds four own pieces on squares of one colour, all free to move the same way along three line
+    types: the only ones that reach the 'eights' plane of the carry-save row counter (loa_sweep.cuh), which every other
+    position skips."""
+    out = []
+    for r in range(8):
+        for pat in (0x55, 0xAA, 0xFF, 0x77):
+            own = pat << (8 * r)
+            far = 1 << (8 * ((r + 4) % 8) + 3)
+            out += [[own, far, 0], [far, own, 1], [own | far << 1 if (far << 1) & ~own else own, far, 0]]
+    return np.array(out, dtype=np.uint64)
+
+
 def test_sweep_movegen_on_host_vs_oracle(hostlib, oracle):
-    S = corpus(oracle, 20000, 0x51EE9)
+    S = np.ascontiguousarray(np.concatenate([corpus(oracle, 20000, 0x51EE9), crowded_rows()]))
     n = len(S)
     counts = np.zeros(n, np.uint8); moves = np.zeros((n, 96, 2), np.uint8)
     hostlib.host_loa_sweep_movegen_batch(ctypes.c_void_p(S.ctypes.data), ctypes.c_uint(n), ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(moves.ctypes.data))
