@@ -2,6 +2,8 @@
 // Hand-written CUDA; integer/branch bound (no tensor cores: nothing here is a contraction).
 #include "loa_sim.cuh"
 #include "kernels.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace loa {
 
@@ -122,12 +124,12 @@ k_rollout(const ulonglong2* __restrict__ boards, const u32* __restrict__ stm, u3
 
 	for (;;) {
 		if (need) {
-			const unsigned grp = __activemask();
-			const int leader = __ffs(grp) - 1;
+			// (coalesced group: well-defined membership under independent thread scheduling, unlike __activemask() + __shfl_sync)
+			const cg::coalesced_group grp = cg::coalesced_threads();
 			unsigned long long base = 0;
-			if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(grp));
-			base = __shfl_sync(grp, base, leader);
-			item = base + __popc(grp & ((1u << lane) - 1u));
+			if (grp.thread_rank() == 0) base = atomicAdd(work_counter, (unsigned long long)grp.size());
+			base = grp.shfl(base, 0);
+			item = base + grp.thread_rank();
 			if (item >= total) break;
 			leaf = (u32)(item / ppl);
 			const ulonglong2 bd = __ldg(boards + leaf);           // LDG.128

@@ -3,6 +3,8 @@
 #include "gameai/philox.h"
 #include "kernels.h"
 #include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace pan {
 
@@ -126,12 +128,13 @@ k_pan_rollout_indep(const uint4* __restrict__ prep, u32 n_leaves, int np, u32 pp
 	const u32 lane = threadIdx.x & 31u;
 	u64 my_plies = 0, my_playouts = 0;
 	for (;;) {
-		const unsigned grp = __activemask();
-		const int leader = __ffs(grp) - 1;
+		// the lanes that arrive here together form one coalesced group (cooperative groups give it a well-defined membership
+		// under independent thread scheduling, which __activemask() + __shfl_sync do not): one atomic per group
+		const cg::coalesced_group grp = cg::coalesced_threads();
 		unsigned long long base = 0;
-		if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(grp));
-		base = __shfl_sync(grp, base, leader);
-		const u64 item = base + __popc(grp & ((1u << lane) - 1u));
+		if (grp.thread_rank() == 0) base = atomicAdd(work_counter, (unsigned long long)grp.size());
+		base = grp.shfl(base, 0);
+		const u64 item = base + grp.thread_rank();
 		if (item >= total) break;
 		const u32 leaf = (u32)(item / ppl);
 		State s;

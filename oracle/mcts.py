@@ -35,8 +35,10 @@ class RefMcts:
                 "seconds": sec.value, "mean_path": mp.value, "sims": runs.value, "sims_per_sec": runs.value / sec.value if sec.value > 0 else 0.0}
 
 
-def ref():
-    if "r" not in _cache:
-        p = os.path.join(_HERE, "_ref", "libref_mcts.so")
-        _cache["r"] = RefMcts(p) if os.path.exists(p) else None
-    return _cache["r"]
+def ref(fastpool=False):
+    """fastpool=True: the build with the stand-in pool allocator (same search, no super-linear slow-down; not for timing)."""
+    k = "f" if fastpool else "r"
+    if k not in _cache:
+        p = os.path.join(_HERE, "_ref", "libref_mcts_fastpool.so" if fastpool else "libref_mcts.so")
+        _cache[k] = RefMcts(p) if os.path.exists(p) else None
+    return _cache[k]

@@ -98,6 +98,21 @@ int gai_loa_rollout(gai_ctx* c, const gai_loa_state* leaves, uint32_t n, uint32_
 }
 int gai_inflight(const gai_ctx* c) { int k = 0; for (int i = 0; i < GAI_MAX_INFLIGHT; ++i) k += c->busy[i]; return k; }
 
+/* Pan: determinized rollouts through the Pan oracle (gai_pan_determinize is host-only code of the real library) */
+uint64_t pan_oracle_playout_batch(int np, const uint64_t* states, uint32_t n_leaves, uint32_t ppl, uint32_t max_plies, int eval_kind,
+                                  uint64_t key, uint64_t first_id, uint32_t* res);
+int gai_pan_rollout(gai_ctx* c, const gai_pan_state* leaves, uint32_t n, int np, uint32_t ppl, uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id,
+                    gai_pan_result* out, gai_rollout_stats* st)
+{
+	if (st) memset(st, 0, sizeof *st);
+	if (n == 0) return GAI_OK;
+	memset(out, 0, sizeof(gai_pan_result) * (size_t)n);
+	const uint64_t plies = pan_oracle_playout_batch(np, (const uint64_t*)leaves, n, ppl, max_plies, eval_kind, key, first_id, (uint32_t*)out);
+	if (st) { st->playouts = (uint64_t)n * ppl; st->plies = plies; st->kernel_ms = st->total_ms = 0.01f; }
+	c->launches += 2;
+	return GAI_OK;
+}
+
 /* single-process stand-ins for the NCCL entry points (world size 1) */
 int gai_comm_unique_id(uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES]) { memset(id, 7, GAI_NCCL_UNIQUE_ID_BYTES); return GAI_OK; }
 int gai_comm_init(gai_ctx* c, int rank, int world, const uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES]) { (void)c; (void)rank; (void)id; return world == 1 ? GAI_OK : GAI_ERR_NCCL; }

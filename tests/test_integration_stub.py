@@ -50,6 +50,6 @@ def test_patched_reference_player_plays_through_the_c_abi_on_the_fake_device():
     src = os.path.join(ROOT, "tests", "helpers", "fake_gpu.c")
     if not os.path.exists(fake) or os.path.getmtime(fake) < os.path.getmtime(src):
         subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", fake, src,
-                               "-L", os.path.join(ROOT, "oracle"), "-lloa_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+                               "-L", os.path.join(ROOT, "oracle"), "-lloa_oracle", "-lpan_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     res = play(3, 64, fake)
     check(res, 3, 64)

@@ -20,7 +20,7 @@ def fake():
     src = os.path.join(ROOT, "tests", "helpers", "fake_gpu.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, src,
-                               "-L", os.path.join(ROOT, "oracle"), "-lloa_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+                               "-L", os.path.join(ROOT, "oracle"), "-lloa_oracle", "-lpan_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     return so
 
 
