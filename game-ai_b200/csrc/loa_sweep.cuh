@@ -68,13 +68,25 @@ GAI_HDI SweepTabs sweep_tabs_host(const uint16_t* lut, const u32* slt, const u32
 #endif
 	return t;
 }
+#ifndef GAI_LUT_ADDR_PRMT
+#define GAI_LUT_ADDR_PRMT 1
+#endif
+__constant__ u32 c_wlut = 2u | (255u << 8) | (255u << 16) | (8u << 24);      // 2 o + (255 + 255 + 8) e = 2 (o + 259 e)
+static_assert(2 * LUT_STRIDE == 255 + 255 + 8, "the enemy-byte weight of the LUT address is the sum of three dp4a byte weights");
 static_assert(2 * LUT_STRIDE == 14 * 37, "the enemy-byte weight of the LUT address is 37 (one dp4a byte) times 14");
 template <int I> GAI_HDI u32 half_of(u64 x) { return I < 4 ? (u32)x : (u32)(x >> 32); }
 template <int I> GAI_HDI u32 lut16(LutRef lut, u64 my, u64 en)          // LUT word of byte I of a rotation
 {
 	const u32 m = half_of<I>(my), e = half_of<I>(en);
 #if defined(__CUDA_ARCH__)
+#if GAI_LUT_ADDR_PRMT
+	// v18: one PRMT puts (own byte, enemy byte x 3) into a register, ONE IDP.4A with the byte weights (2, 255, 255, 8)
+	// gives 2 o + 518 e + base: three instructions per lookup (PRMT, IDP.4A, LDS) instead of four
+	constexpr u32 SEL = (u32)(I & 3) | ((u32)(4 + (I & 3)) * 0x1110u);
+	const u32 a = hd_dp4a(hd_byte_perm(m, e, SEL), c_wlut, lut);
+#else
 	const u32 a = hd_dp4a(e, c_wt.w37[I & 3], 0u) * c_14 + hd_dp4a(m, c_wt.w2[I & 3], lut);
+#endif
 	u32 v;
 	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
