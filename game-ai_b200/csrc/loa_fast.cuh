@@ -218,11 +218,12 @@ GAI_HDI bool apply_move_sweep(Side& my, Side& en, int from, int to, const u64* _
 
 // apply for the sweep kernel with the Euler characteristics of both colours kept up to date (loa_euler.cuh): the mover's
 // figure loses `from` and gains `to`, the other colour loses `to` on a capture.  Returns true on a capture.
-GAI_HDI bool apply_move_chi(Side& my, Side& en, int& chi_my, int& chi_en, int from, int to, const u64* __restrict__ sqt,
-                            const u64* __restrict__ nbx, const signed char* __restrict__ chitab)
+// hf / ht: the rotated positions of from / to (high word of the square table); wf / wt: their window controls (loa_euler.cuh).
+// The caller loads them: the rollout kernel from per-lane copies of the two tables (conflict-free), everything else from
+// the plain 64-entry tables through the overload below.
+GAI_HDI bool apply_move_chi(Side& my, Side& en, int& chi_my, int& chi_en, int from, int to, u32 hf, u32 ht, u64 wf, u64 wt,
+                            const signed char* __restrict__ chitab)
 {
-	const u64 wf = nbx[from], wt = nbx[to];
-	const u32 hf = (u32)(sqt[from] >> 32), ht = (u32)(sqt[to] >> 32);
 	const u64 tR = bit64(to), tC = bit64((int)hd_dp4a(ht, 0x00000001u, 0u)), t1 = bit64((int)hd_dp4a(ht, 0x00000100u, 0u)), t2 = bit64((int)hd_dp4a(ht, 0x00010000u, 0u));
 	const bool cap = (en.R & tR) != 0;
 	const int d_from = chitab[chi_index(my.R, wf)];               // the centre is masked out of its own neighbourhood
@@ -237,6 +238,11 @@ GAI_HDI bool apply_move_chi(Side& my, Side& en, int& chi_my, int& chi_en, int fr
 	my.D2 = (my.D2 ^ bit64((int)hd_dp4a(hf, 0x00010000u, 0u))) | t2;
 	en.R &= ~tR; en.C &= ~tC; en.D1 &= ~t1; en.D2 &= ~t2;
 	return cap;
+}
+GAI_HDI bool apply_move_chi(Side& my, Side& en, int& chi_my, int& chi_en, int from, int to, const u64* __restrict__ sqt,
+                            const u64* __restrict__ nbx, const signed char* __restrict__ chitab)
+{
+	return apply_move_chi(my, en, chi_my, chi_en, from, to, (u32)(sqt[from] >> 32), (u32)(sqt[to] >> 32), nbx[from], nbx[to], chitab);
 }
 
 } // namespace loa

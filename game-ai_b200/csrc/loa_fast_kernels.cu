@@ -17,15 +17,22 @@ __constant__ ChiTable c_chi = make_chi_table();
 struct FastSmem {
 	const uint16_t* lut; const u64* sqt; const u64* lines; const u64* ld; const u64* rd; const u64* nbr; const u32* slt; const u32* tpc;
 	const u64* nbx; const signed char* chi;
+	const u64* nbxl; const u32* posl;          // this lane's column of the per-lane copies (static-sweep kernels)
 };
 
 // dynamic shared memory: [LUT_BYTES lut][64 x u64 sqt][4 x 64 x u64 line masks: row, column, ld, rd][64 x u64 neighbourhoods]
 //                        [64 x u64 window controls (loa_euler.cuh)][384 B chi deltas][tail]
 //   tail of the static-sweep kernels : [256 x 32 lanes x u32 short-line table][256 x 32 x u32 field-count table]
+//                                      [64 x 32 lanes x u64 window controls][64 x 32 lanes x u32 rotated positions]
+//                                      (per-lane copies: entry pitch 256 B / 128 B, lane L only touches its own banks; ncu on v18:
+//                                      the plain 512-byte tables cost 4.9 wavefronts per LDS.64 and 3.2 per LDS.32, and the
+//                                      LSU data pipe, not the issue rate, had become the first limit)
 //   tail of the per-piece kernels    : [16 x 1024 bytes piece squares]
 constexpr int FAST_SQ_OFF = LUT_BYTES + 7 * 64 * 8 + CHI_TAB_SIZE;
 constexpr int FAST_SMEM_BYTES = FAST_SQ_OFF + 16 * 1024;
-constexpr int SWEEP_SMEM_BYTES = FAST_SQ_OFF + 2 * 256 * 32 * 4;
+constexpr int SWEEP_PERLANE_OFF = FAST_SQ_OFF + 2 * 256 * 32 * 4;
+constexpr int SWEEP_SMEM_BYTES = SWEEP_PERLANE_OFF + 64 * 32 * 8 + 64 * 32 * 4;
+static_assert(SWEEP_SMEM_BYTES <= 227 * 1024, "sweep kernel shared memory");
 
 // g_lut = the global image: line LUT, then the two 256-entry tables (expanded here to one copy per lane / bank)
 template <bool SWEEP_TABLES>
@@ -43,12 +50,16 @@ __device__ __forceinline__ FastSmem load_fast_smem(unsigned char* smem, const ui
 	for (int i = threadIdx.x; i < CHI_TAB_SIZE; i += blockDim.x) chi[i] = c_chi.d[i];
 	FastSmem f; f.lut = reinterpret_cast<const uint16_t*>(smem); f.sqt = sq; f.lines = sq + 64; f.ld = sq + 192; f.rd = sq + 256; f.nbr = sq + 320;
 	f.nbx = sq + 384; f.chi = chi;
-	f.slt = f.tpc = nullptr;
+	f.slt = f.tpc = nullptr; f.nbxl = nullptr; f.posl = nullptr;
 	if (SWEEP_TABLES) {
 		u32* t = reinterpret_cast<u32*>(smem + FAST_SQ_OFF);
 		const u32* g = reinterpret_cast<const u32*>(reinterpret_cast<const unsigned char*>(g_lut) + SLT_OFF);      // 512 words: slt, tpc
 		for (int i = threadIdx.x; i < 2 * 256 * 32; i += blockDim.x) t[i] = __ldg(g + (i >> 5));
 		f.slt = t; f.tpc = t + 256 * 32;
+		u64* nl = reinterpret_cast<u64*>(smem + SWEEP_PERLANE_OFF);
+		u32* pl = reinterpret_cast<u32*>(smem + SWEEP_PERLANE_OFF + 64 * 32 * 8);
+		for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) { nl[i] = c_nbx.w[i >> 5]; pl[i] = (u32)(c_sqt.w[i >> 5] >> 32); }
+		f.nbxl = nl + (threadIdx.x & 31); f.posl = pl + (threadIdx.x & 31);
 	}
 	__syncthreads();
 	return f;
@@ -242,7 +253,7 @@ __device__ __forceinline__ int wstep_sweep(Side& my, Side& en, int& chi_my, int&
 	if (play) {
 		if (n != 0) {
 			const int to = move_target_tab(my.R | en.R, from, dir, f.lines);
-			apply_move_chi(my, en, chi_my, chi_en, from, to, f.sqt, f.nbx, f.chi);
+			apply_move_chi(my, en, chi_my, chi_en, from, to, f.posl[32 * from], f.posl[32 * to], f.nbxl[32 * from], f.nbxl[32 * to], f.chi);
 		}
 		ply += 1;
 	}

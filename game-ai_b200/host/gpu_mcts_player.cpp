@@ -518,7 +518,8 @@ struct GpuMctsPlayer : IGamePlayer
 				throw msg.c_str();                             // no CPU fallback: the player cannot play without its GPU
 			}
 		}
-		if (world > 1) init_comm();
+		// GAI_FORCE_COMM: a single rank still goes through the NCCL communicator (lets a one-GPU box exercise the merge path)
+		if (world > 1 || getenv("GAI_FORCE_COMM")) init_comm();
 	}
 	// rank 0 writes the NCCL unique id to GAI_NCCL_ID_FILE, the other ranks poll for it.  A file left over from a
 	// crashed run is not accepted: rank 0 removes it before writing (and when it exits), the others only take a file
@@ -526,7 +527,7 @@ struct GpuMctsPlayer : IGamePlayer
 	void init_comm()
 	{
 		const char* path = getenv("GAI_NCCL_ID_FILE");
-		if (!path) throw "gpumctsplayer: WORLD_SIZE > 1 needs GAI_NCCL_ID_FILE";
+		if (!path) throw "gpumctsplayer: WORLD_SIZE > 1 (or GAI_FORCE_COMM) needs GAI_NCCL_ID_FILE";
 		id_file = path;
 		uint8_t id[GAI_NCCL_UNIQUE_ID_BYTES];
 		if (rank == 0) {

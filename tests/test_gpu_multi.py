@@ -37,3 +37,21 @@ def test_two_ranks_play_the_same_game():
         st = [r["players"][0]["stats"] for r in res]
         assert st[0]["last_root_stats"] == st[1]["last_root_stats"]
         assert res[0]["players"][0]["lose"] == 0
+
+
+def test_one_rank_goes_through_the_nccl_merge_on_a_one_gpu_box():
+    """The same merge path with a communicator of ONE rank (GAI_FORCE_COMM): ncclCommInitRank + the per-move
+    gai_allreduce_root run on whatever single GPU the box has, and -- the sum over one rank being the identity -- the game is
+    move for move the one played without a communicator."""
+    def play(extra_env):
+        env = dict(os.environ, **extra_env)
+        r = subprocess.run([LAUNCHER, "--xml", XML, "--p1", "mcts devices=0 move_sim_limit=65536 random_seed=5 philox_seed=6",
+                            "--p2", "random random_seed=7", "--ng", "1", "--rl", "16", "--seed", "11", "-v"], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [l for l in r.stdout.splitlines() if l.startswith("round ")], json.loads(r.stdout.strip().splitlines()[-1])
+    with tempfile.TemporaryDirectory() as tmp:
+        m1, r1 = play({"WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0", "GAI_FORCE_COMM": "1", "GAI_NCCL_ID_FILE": os.path.join(tmp, "nccl_id")})
+    m0, r0 = play({})
+    assert len(m1) >= 8 and m1 == m0
+    assert float(r1["players"][0]["stats"]["allreduce_us_per_move"]) > 0.0
+    assert float(r0["players"][0]["stats"]["allreduce_us_per_move"]) == 0.0

@@ -106,3 +106,39 @@ def test_cycle_score_and_terminal_root(fake):
     # a terminal root: the player hands back the rules' list instead of searching (no crash, no move from an empty list)
     r = run(fake, "--p1", "random", "--p2", "mcts move_sim_limit=100", "--ng", "1", "--rl", "1", "--start", "0x3,0x0c00000000000000,1", check=False)
     assert r.returncode == 0, r.stderr[-500:]
+
+
+PAN_XML = os.path.join(ROOT, "run_config_pan.xml")
+
+
+@pytest.mark.parametrize("mode", ["tree", "flat"])
+def test_pan_determinized_player_host_logic(fake, mode):
+    """gpu_pan_player.cpp on the fake device: the shared tree over sampled deals (and round 1's flat evaluation) runs a
+    three-player game against two lowcard players, every decision gets its deals (no determinization fallback on fresh
+    games), the playouts the device reports are the ones the player asked for, and a fixed seed replays the same game."""
+    spec = "gpupan mode=%s move_sim_limit=256 gpu_batch=32 deals=16 playouts_per_leaf=4 random_seed=9 philox_seed=10" % mode
+    a = run(fake, "--p1", spec, "--p2", "lowcard", "--p3", "lowcard", "--ng", "1", "--rl", "24", "--seed", "6", "-q", xml=PAN_XML)
+    b = run(fake, "--p1", spec, "--p2", "lowcard", "--p3", "lowcard", "--ng", "1", "--rl", "24", "--seed", "6", "-q", xml=PAN_XML)
+    st = a["players"][0]["stats"]
+    assert float(st["decisions"]) > 0 and float(st["determinization_fallbacks"]) == 0 and float(st["devices"]) == 1
+    assert float(st["playouts"]) > 0 and float(st["playouts"]) % 4 == 0
+    if mode == "tree":
+        assert float(st["iterations"]) >= float(st["decisions"]) and float(st["tree_nodes"]) >= 1
+    assert a["rounds"] == b["rounds"] and a["first_move"] == b["first_move"]
+    assert [p["pts"] for p in a["players"]] == [p["pts"] for p in b["players"]]
+    assert st["playouts"] == b["players"][0]["stats"]["playouts"]
+
+
+def test_single_rank_communicator_is_the_identity(fake, tmp_path):
+    """GAI_FORCE_COMM: one rank through the merge path (communicator init, per-move all-reduce with its position checksum) plays
+    the same game as no communicator at all; tests/test_gpu_multi.py runs the same pair against NCCL on a GPU."""
+    args = ("--p1", "mcts devices=0 move_sim_limit=1024 random_seed=5 philox_seed=6", "--p2", "random random_seed=7", "--ng", "1", "--rl", "8", "--seed", "11", "-v")
+    def play(extra):
+        env = dict(os.environ, LD_PRELOAD=fake, **extra)
+        r = subprocess.run([LAUNCHER, "--xml", XML] + list(args), capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [l for l in r.stdout.splitlines() if l.startswith("round ")], json.loads(r.stdout.strip().splitlines()[-1])
+    m1, r1 = play({"WORLD_SIZE": "1", "RANK": "0", "GAI_FORCE_COMM": "1", "GAI_NCCL_ID_FILE": str(tmp_path / "id")})
+    m0, r0 = play({})
+    assert len(m0) >= 4 and m0 == m1
+    assert float(r1["players"][0]["stats"]["allreduce_us_per_move"]) > 0 and float(r0["players"][0]["stats"]["allreduce_us_per_move"]) == 0
