@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-player", action="store_true", help="skip the config-4 player leg")
     ap.add_argument("--no-pan", action="store_true", help="skip the config-5 Pan leg")
     ap.add_argument("--player-moves", type=int, default=12, help="move decisions of the GPU player in the player leg")
+    ap.add_argument("--player-trees", type=int, default=2, help="root-parallel trees per GPU in the player leg (one host thread, context and stream each)")
     ap.add_argument("--player-args", default="", help="extra key=value tokens for the player leg's mcts player")
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
@@ -258,7 +259,7 @@ def player_leg(args, rank, world, local, dist):
     if dist:
         dist.broadcast_object_list(idf, src=0)
     env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(local), GAI_NCCL_ID_FILE=idf[0])
-    spec = "mcts devices= move_time_limit=1 random_seed=5 philox_seed=6 " + args.player_args
+    spec = "mcts devices= trees_per_gpu=%d move_time_limit=1 random_seed=5 philox_seed=6 " % args.player_trees + args.player_args
     cmd = [LAUNCHER, "--xml", os.path.join(ROOT, "run_config_loa.xml"), "--p1", "random random_seed=7", "--p2", spec.strip(),
            "--ng", "1", "--rl", str(2 * args.player_moves), "--seed", "11", "-v"]
     if dist:
@@ -285,7 +286,8 @@ def player_leg(args, rank, world, local, dist):
         return None
     ok = all(x["rc"] == 0 for x in allr)
     out = {"what": "config 4: root-parallel gpumctsplayer (run_config_loa.xml 'mcts' parameters, provider swapped), Blacks, from the opening vs a fixed-seed random mover; "
-                   "%d move decisions at move_time_limit=1; one rank per GPU, own tree and Philox stream per rank, gai_allreduce_root (NCCL) once per move decision" % args.player_moves,
+                   "%d move decisions at move_time_limit=1; one rank per GPU, %d root-parallel tree(s) per rank (own host thread, context, stream and Philox stream each, summed at the root), "
+                   "gai_allreduce_root (NCCL) across ranks once per move decision" % (args.player_moves, args.player_trees), "trees_per_gpu": args.player_trees,
            "ranks": allr, "n_ranks": world, "ok": ok}
     if ok:
         out["total_playouts_per_sec"] = sum(x["playouts_per_sec"] for x in allr)
