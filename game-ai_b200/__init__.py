@@ -83,6 +83,7 @@ def lib():
         L.gai_pan_apply.argtypes = [_vp, _vp, _vp, _u32, _i32, _vp]
         L.gai_pan_terminal.argtypes = [_vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]
         L.gai_pan_rollout.argtypes = [_vp, _vp, _u32, _i32, _u32, _u32, _i32, _u64, _u64, _vp, _vp]
+        L.gai_pan_rollout_device.argtypes = [_vp, _vp, _u32, _i32, _u32, _u32, _i32, _u64, _u64, _vp, _vp]
         L.gai_pan_playout_trace.argtypes = [_vp, _vp, _u32, _i32, _u32, _i32, _u64, _u64, _vp, _vp, _vp, _vp]
         L.gai_pan_determinize.argtypes = [_vp, _i32, _i32, _u32, _u64, _u64, _vp]
         L.gai_dev_alloc.argtypes = [_vp, _u64, ctypes.POINTER(_vp)]
@@ -316,6 +317,22 @@ class GpuRollout:
         self._ck(self.L.gai_pan_rollout(self.h, s.ctypes.data, n, num_players, playouts_per_leaf, max_plies, eval_kind, key, first_id,
                                         r.ctypes.data, ctypes.byref(st)))
         return r, _stats(st)
+
+    def pan_rollout_into(self, num_players, states, out, playouts_per_leaf=1, max_plies=50, eval_kind=1, key=0x10A5EED, first_id=0):
+        """gai_pan_rollout with caller-owned buffers (pinned ones are DMA-ed in place): states (n,5) uint64, out (n,12) uint32"""
+        assert states.dtype == np.uint64 and states.flags.c_contiguous and out.dtype == np.uint32 and out.flags.c_contiguous
+        n = states.shape[0]; st = RolloutStats()
+        assert out.size == 12 * n
+        self._ck(self.L.gai_pan_rollout(self.h, states.ctypes.data, n, num_players, playouts_per_leaf, max_plies, eval_kind, key, first_id,
+                                        out.ctypes.data, ctypes.byref(st)))
+        return _stats(st)
+
+    def pan_rollout_device(self, num_players, d_states, n, d_out, playouts_per_leaf=1, max_plies=50, eval_kind=1, key=0x10A5EED, first_id=0):
+        """Inputs resident in HBM (raw device pointers as ints): n x 40-byte states in, n x 48-byte results out. -> stats dict"""
+        st = RolloutStats()
+        self._ck(self.L.gai_pan_rollout_device(self.h, d_states, n, num_players, playouts_per_leaf, max_plies, eval_kind, key, first_id,
+                                               d_out, ctypes.byref(st)))
+        return _stats(st)
 
     def pan_playout_trace(self, num_players, states, max_plies=50, eval_kind=1, key=0x10A5EED, first_id=0):
         s = self._pstates(states); n = s.shape[0]

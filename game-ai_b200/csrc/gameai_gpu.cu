@@ -1,6 +1,7 @@
 // game-ai_b200/csrc/gameai_gpu.cu -- C ABI of libgameai_gpu.so (see include/gameai_gpu.h).
 // Context = one device, one stream, pinned staging + device scratch grown on demand.  No CPU fallback.
 #include "gameai_gpu.h"
+#include <algorithm>
 #include "kernels.h"
 #include "gameai/philox.h"
 #include <cuda_runtime.h>
@@ -45,6 +46,9 @@ struct Slot {
 	gai_loa_result* out = nullptr; uint32_t n_out = 0; unsigned gen = 0;
 };
 
+constexpr int GAI_PAN_MAX_CHUNKS = 32;
+constexpr uint32_t GAI_PAN_CHUNK = 65536;          // deals per pipeline stage (2.6 MB in, 3 MB out, ~0.4 ms of kernel at depth 50)
+
 struct gai_ctx {
 	int device = 0;
 	Slot slots[GAI_MAX_INFLIGHT];
@@ -64,6 +68,10 @@ struct gai_ctx {
 	Buf h_in, h_in2, h_out, h_out2, h_out3;
 	// async rollout bookkeeping
 	gai_loa_result* pending_out = nullptr; uint32_t pending_n = 0; bool pending_direct = false;   // direct: results were DMA-ed into the caller's pinned buffer
+	// Pan host-buffer pipeline (gai_pan_rollout): copy-in and copy-out streams beside the compute stream, events per chunk
+	cudaStream_t pan_in = nullptr, pan_out = nullptr;
+	cudaEvent_t pan_ev[4][GAI_PAN_MAX_CHUNKS] = {};      // [0] chunk uploaded, [1] kernels start, [2] kernels end, [3] chunk downloaded
+	Buf pan_misc;                                         // 64 bytes per chunk: {playouts, plies, work counter}, then the bad-state flag
 	// nccl
 	NcclApi nccl; ncclComm_t comm = nullptr; int rank = 0, world = 1;
 };
@@ -239,6 +247,10 @@ void gai_destroy(gai_ctx* ctx)
 		for (auto& ev : sl.ev) if (ev) cudaEventDestroy(ev);
 	}
 	if (ctx->d_lut) cudaFree(ctx->d_lut);
+	release(ctx->pan_misc);
+	for (auto& row : ctx->pan_ev) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
+	if (ctx->pan_in) cudaStreamDestroy(ctx->pan_in);
+	if (ctx->pan_out) cudaStreamDestroy(ctx->pan_out);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -731,6 +743,11 @@ int gai_pan_terminal(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int 
 	return pan_bad(ctx, bad);
 }
 
+// Host buffers in, host buffers out, in pipeline stages of GAI_PAN_CHUNK deals: stage c+1 is uploaded (own copy stream) while
+// stage c plays out (compute stream) and stage c-1 is downloaded (second copy stream); a pageable buffer is staged through pinned
+// memory one stage at a time, a PINNED caller buffer is DMA-ed in place.  Deals are independent, a playout's identity is
+// (key, first_id + leaf * ppl + j): the stages change nothing in the results.  stats->kernel_ms = the stages' kernel time (all
+// kernels run back to back on the one compute stream), total_ms = first upload to last download.
 int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves, int np, uint32_t ppl,
                     uint32_t max_plies, int eval_kind, uint64_t key, uint64_t first_id, gai_pan_result* out, gai_rollout_stats* stats)
 {
@@ -743,28 +760,101 @@ int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves
 	if (eval_kind != 0 && eval_kind != 1) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout: eval_kind must be 0 (num_cards) or 1 (num_cards_weighted)");
 	CU(cudaSetDevice(ctx->device));
 	QUIESCE("gai_pan_rollout");
+	if (!ctx->pan_in) {
+		CU(cudaStreamCreateWithFlags(&ctx->pan_in, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&ctx->pan_out, cudaStreamNonBlocking));
+		for (int k = 0; k < 4; ++k) for (int c = 0; c < GAI_PAN_MAX_CHUNKS; ++c)
+			CU(cudaEventCreateWithFlags(&ctx->pan_ev[k][c], (k == 1 || k == 2) ? cudaEventDefault : cudaEventDisableTiming));
+	}
+	uint32_t chunk = GAI_PAN_CHUNK;
+	if ((n_leaves + chunk - 1) / chunk > (uint32_t)GAI_PAN_MAX_CHUNKS) chunk = (n_leaves + GAI_PAN_MAX_CHUNKS - 1) / GAI_PAN_MAX_CHUNKS;
+	const int nch = (int)((n_leaves + chunk - 1) / chunk);
 	const size_t sb = (size_t)n_leaves * 40, rb = (size_t)n_leaves * sizeof(gai_pan_result);
-	EN(ctx->h_in, sb, true); EN(ctx->h_out, rb, true);
-	EN(ctx->d_in, sb, false); EN(ctx->d_out, rb, false); EN(ctx->d_misc, 64, false); EN(ctx->d_prep, (size_t)n_leaves * 32, false);
-	memcpy(ctx->h_in.p, leaves, sb);
+	cudaPointerAttributes pa{}, po{};
+	const bool pin_in = cudaPointerGetAttributes(&pa, leaves) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	const bool pin_out = cudaPointerGetAttributes(&po, out) == cudaSuccess && po.type == cudaMemoryTypeHost;
+	cudaGetLastError();                                   // a pageable pointer leaves an error behind on old drivers
+	if (!pin_in) EN(ctx->h_in, sb, true);
+	if (!pin_out) EN(ctx->h_out, rb, true);
+	EN(ctx->d_in, sb, false); EN(ctx->d_out, rb, false); EN(ctx->d_prep, (size_t)n_leaves * 32, false);
+	EN(ctx->pan_misc, 64 * (size_t)(GAI_PAN_MAX_CHUNKS + 1), false);
+	uint32_t* d_bad = (uint32_t*)((char*)ctx->pan_misc.p + 64 * (size_t)GAI_PAN_MAX_CHUNKS);
+	const char* src = pin_in ? (const char*)leaves : (const char*)ctx->h_in.p;
+	char* dst = pin_out ? (char*)out : (char*)ctx->h_out.p;
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-	CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, sb, cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
+	CU(cudaStreamWaitEvent(ctx->pan_in, ctx->ev[0], 0));
+	CU(cudaMemsetAsync(ctx->pan_misc.p, 0, 64 * (size_t)(GAI_PAN_MAX_CHUNKS + 1), ctx->stream));
 	CU(cudaMemsetAsync(ctx->d_out.p, 0, rb, ctx->stream));
+	for (int c = 0; c < nch; ++c) {
+		const uint32_t off = (uint32_t)c * chunk, nc = std::min(chunk, n_leaves - off);
+		if (!pin_in) memcpy((char*)ctx->h_in.p + (size_t)off * 40, (const char*)leaves + (size_t)off * 40, (size_t)nc * 40);
+		CU(cudaMemcpyAsync((char*)ctx->d_in.p + (size_t)off * 40, src + (size_t)off * 40, (size_t)nc * 40, cudaMemcpyHostToDevice, ctx->pan_in));
+		CU(cudaEventRecord(ctx->pan_ev[0][c], ctx->pan_in));
+		CU(cudaStreamWaitEvent(ctx->stream, ctx->pan_ev[0][c], 0));
+		CU(cudaEventRecord(ctx->pan_ev[1][c], ctx->stream));
+		const uint64_t total = (uint64_t)nc * ppl;
+		int blocks = ctx->prop.multiProcessorCount * 8;
+		if ((total + 255) / 256 < (uint64_t)blocks) blocks = (int)((total + 255) / 256);
+		uint64_t* d_st = (uint64_t*)((char*)ctx->pan_misc.p + 64 * (size_t)c);
+		launch_pan_rollout((char*)ctx->d_in.p + (size_t)off * 40, (char*)ctx->d_prep.p + (size_t)off * 32, nc, np, ppl, max_plies, eval_kind, key,
+		                   first_id + (uint64_t)off * ppl, (uint32_t*)((char*)ctx->d_out.p + (size_t)off * sizeof(gai_pan_result)),
+		                   d_st, (unsigned long long*)d_st + 2, d_bad, blocks, ctx->stream);
+		LAUNCHED("k_pan_prepare"); LAUNCHED("k_pan_rollout");
+		CU(cudaEventRecord(ctx->pan_ev[2][c], ctx->stream));
+		CU(cudaStreamWaitEvent(ctx->pan_out, ctx->pan_ev[2][c], 0));
+		CU(cudaMemcpyAsync(dst + (size_t)off * sizeof(gai_pan_result), (char*)ctx->d_out.p + (size_t)off * sizeof(gai_pan_result),
+		                   (size_t)nc * sizeof(gai_pan_result), cudaMemcpyDeviceToHost, ctx->pan_out));
+		CU(cudaEventRecord(ctx->pan_ev[3][c], ctx->pan_out));
+	}
+	CU(cudaStreamWaitEvent(ctx->stream, ctx->pan_ev[3][nch - 1], 0));
+	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+	for (int c = 0; c < nch; ++c) {                        // a pageable `out` is filled stage by stage while later stages still run
+		CU(cudaEventSynchronize(ctx->pan_ev[3][c]));
+		const uint32_t off = (uint32_t)c * chunk, nc = std::min(chunk, n_leaves - off);
+		if (!pin_out) memcpy((char*)out + (size_t)off * sizeof(gai_pan_result), (char*)ctx->h_out.p + (size_t)off * sizeof(gai_pan_result), (size_t)nc * sizeof(gai_pan_result));
+	}
+	CU(cudaStreamSynchronize(ctx->stream));
+	uint64_t h[8 * GAI_PAN_MAX_CHUNKS + 8];
+	CU(cudaMemcpy(h, ctx->pan_misc.p, 64 * (size_t)(GAI_PAN_MAX_CHUNKS + 1), cudaMemcpyDeviceToHost));
+	r = pan_bad(ctx, (uint32_t)h[8 * GAI_PAN_MAX_CHUNKS]); if (r) return r;
+	if (stats) {
+		for (int c = 0; c < nch; ++c) {
+			stats->playouts += h[8 * c]; stats->plies += h[8 * c + 1];
+			float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->pan_ev[1][c], ctx->pan_ev[2][c])); stats->kernel_ms += ms;
+		}
+		CU(cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
+	}
+	return GAI_OK;
+}
+
+int gai_pan_rollout_device(gai_ctx* ctx, const void* d_states, uint32_t n_leaves, int np, uint32_t ppl, uint32_t max_plies, int eval_kind,
+                           uint64_t key, uint64_t first_id, void* d_out, gai_rollout_stats* stats)
+{
+	if (!ctx) return GAI_ERR_INVALID;
+	if (stats) memset(stats, 0, sizeof *stats);
+	int r = pan_check_np(ctx, np); if (r) return r;
+	if (n_leaves == 0) return GAI_OK;
+	if (!d_states || !d_out) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout_device: NULL buffer");
+	if (ppl == 0) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout_device: playouts_per_leaf must be >= 1");
+	if (eval_kind != 0 && eval_kind != 1) return fail(ctx, GAI_ERR_INVALID, "gai_pan_rollout_device: eval_kind must be 0 (num_cards) or 1 (num_cards_weighted)");
+	CU(cudaSetDevice(ctx->device));
+	QUIESCE("gai_pan_rollout_device");
+	EN(ctx->d_misc, 64, false); EN(ctx->d_prep, (size_t)n_leaves * 32, false);
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	CU(cudaMemsetAsync(ctx->d_misc.p, 0, 64, ctx->stream));
+	CU(cudaMemsetAsync(d_out, 0, (size_t)n_leaves * sizeof(gai_pan_result), ctx->stream));
 	const uint64_t total = (uint64_t)n_leaves * ppl;
 	int blocks = ctx->prop.multiProcessorCount * 8;
 	if ((total + 255) / 256 < (uint64_t)blocks) blocks = (int)((total + 255) / 256);
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-	launch_pan_rollout(ctx->d_in.p, ctx->d_prep.p, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, (uint32_t*)ctx->d_out.p,
+	launch_pan_rollout(d_states, ctx->d_prep.p, n_leaves, np, ppl, max_plies, eval_kind, key, first_id, (uint32_t*)d_out,
 	                   (uint64_t*)ctx->d_misc.p, (unsigned long long*)ctx->d_misc.p + 2, PAN_BAD_PTR, blocks, ctx->stream);
 	LAUNCHED("k_pan_prepare"); LAUNCHED("k_pan_rollout");
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	uint32_t bad = 0;
-	CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, rb, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(&bad, PAN_BAD_PTR, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	memcpy(out, ctx->h_out.p, rb);
 	r = pan_bad(ctx, bad); if (r) return r;
 	return fill_stats(ctx, stats, true);
 }

@@ -185,6 +185,12 @@ int gai_pan_terminal(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int 
 int gai_pan_rollout(gai_ctx* ctx, const gai_pan_state* leaves, uint32_t n_leaves, int num_players, uint32_t playouts_per_leaf,
                     uint32_t max_plies, int eval_kind, uint64_t philox_key, uint64_t first_playout_id,
                     gai_pan_result* out, gai_rollout_stats* stats);
+/* DEVICE-resident variant (inputs already in HBM): d_states = n_leaves x gai_pan_state (40 B each), d_out = n_leaves x
+ * gai_pan_result (zeroed by the call); one pass on the ctx stream, synchronises, fills stats.  The host-buffer call above
+ * moves the same data in pipeline stages of 65536 deals (upload / play out / download overlapped). */
+int gai_pan_rollout_device(gai_ctx* ctx, const void* d_states, uint32_t n_leaves, int num_players, uint32_t playouts_per_leaf,
+                           uint32_t max_plies, int eval_kind, uint64_t philox_key, uint64_t first_playout_id,
+                           void* d_out, gai_rollout_stats* stats);
 /* single playouts with detail: code[i] = loser 0..3, or 4 for a capped playout; value = Score / eval at the end */
 int gai_pan_playout_trace(gai_ctx* ctx, const gai_pan_state* states, uint32_t n, int num_players, uint32_t max_plies, int eval_kind,
                           uint64_t philox_key, uint64_t first_playout_id, uint8_t* code, uint32_t* plies, int32_t* value,

@@ -121,3 +121,36 @@ def test_both_rollout_kernels_agree(gpu, po):
             assert (orr == got[1][0][:500]).all()
     finally:
         os.environ.pop("GAI_PAN_KERNEL", None)
+
+
+def test_host_buffer_pipeline_stages_agree_with_one_pass(gpu, po):
+    """gai_pan_rollout moves a large batch in overlapped stages of 65536 deals (upload / kernels / download on three streams):
+    pageable and pinned caller buffers, a ragged last stage, and the device-resident single pass must give the same per-deal
+    results and totals; a strided sample is checked against the oracle with the same playout ids."""
+    import torch
+    import gameai_b200 as g
+    npl, n, ppl = 3, 2 * 65536 + 4097, 4
+    view = np.zeros(5, np.uint64)
+    own = 0
+    for c in (1, 4, 7, 10, 13, 16, 19, 22):
+        own |= 3 << (2 * c)
+    view[0] = np.uint64(1 << 48); view[1] = np.uint64(8 | (own << 4)); view[2] = np.uint64(8); view[3] = np.uint64(8)
+    D = g.pan_determinize(view, npl, 0, n, 1234, 0)
+    r_page, st_page = gpu.pan_rollout(npl, D, ppl, 50, 1, 99, 5000)                          # pageable in / out
+    pin_in = torch.from_numpy(D.view(np.int64)).pin_memory().numpy().view(np.uint64)
+    r_pin = torch.zeros((n, 12), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    st_pin = gpu.pan_rollout_into(npl, pin_in, r_pin, ppl, 50, 1, 99, 5000)                  # pinned: DMA in place
+    d_s = gpu.dev_alloc(n * 40); d_r = gpu.dev_alloc(n * 48)
+    try:
+        gpu.h2d(d_s, D)
+        st_dev = gpu.pan_rollout_device(npl, d_s, n, d_r, ppl, 50, 1, 99, 5000)
+        r_dev = np.zeros((n, 12), np.uint32); gpu.d2h(r_dev, d_r)
+    finally:
+        gpu.dev_free(d_s); gpu.dev_free(d_r)
+    assert (r_page == r_dev).all() and (r_pin == r_dev).all()
+    assert st_page["playouts"] == st_pin["playouts"] == st_dev["playouts"] == n * ppl
+    assert st_page["plies"] == st_pin["plies"] == st_dev["plies"]
+    idx = np.arange(0, n, 997)
+    for i in idx[:80]:
+        orr, _ = po.playout_batch(npl, D[i:i + 1], ppl, 50, 1, 99, 5000 + int(i) * ppl)
+        assert (orr[0] == r_dev[i]).all(), i
