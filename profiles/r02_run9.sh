@@ -16,5 +16,5 @@ run() {
 run "move_sim_limit=16384 eval_function=num_cards playout_depth=100"
 run "move_sim_limit=16384 playout_depth=1000"
 run "move_sim_limit=16384 eval_function=num_cards explore_exploit_ratio=0.35"
-timeout 2400 python profiles/tier3_match.py 64 200 16 > gpurun_out/r02_tier3_match.json 2> gpurun_out/r02_tier3_match.err; echo "tier3 rc=$?"
+timeout 2400 python tests/tools/tier3_match.py 64 200 16 > gpurun_out/r02_tier3_match.json 2> gpurun_out/r02_tier3_match.err; echo "tier3 rc=$?"
 tail -14 gpurun_out/r02_tier3_match.json

@@ -2,10 +2,10 @@
 """Pan determinized-rollout throughput on one B200 (config 5 of BASELINE.json), with the reference rules timed beside it.
 MEASUREMENT SCRIPT, not product: oracle/ serves as corpus generator, as the checker of the first 2048 deals and as the
 CPU baseline beside the GPU number (like bench.py's cpu_baseline leg).
-usage (GPU box): python profiles/pan_bench.py > gpurun_out/pan_bench.json"""
+usage (GPU box): python tests/tools/pan_bench.py > gpurun_out/pan_bench.json"""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import gameai_b200 as g
 from oracle import pan
 

@@ -5,10 +5,10 @@ formulations of the rules, with the reference rules on one host core beside it. 
 (tests/test_gpu_rules.py::test_full_size_sweep_1m_positions); this script only times it.
 MEASUREMENT SCRIPT, not product: oracle/ serves as corpus generator and as the one-core CPU baseline (like bench.py's
 cpu_baseline leg).
-usage (GPU box): python profiles/rules_sweep_bench.py > gpurun_out/rules_sweep.json"""
+usage (GPU box): python tests/tools/rules_sweep_bench.py > gpurun_out/rules_sweep.json"""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import gameai_b200 as g
 from oracle import loa
 

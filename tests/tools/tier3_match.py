@@ -2,9 +2,9 @@
 """Tier 3, win rate: the GPU-backed player in its reference-like mode against the reference's own MC::Player (test-only plugin
 oracle/_ref/librefmctsplayer.so) at the same simulation budget, both colours, with reference-vs-reference as the control and both
 against a random mover (aborted-game rates).  MEASUREMENT SCRIPT (test infrastructure: it loads oracle/_ref).
-usage: python profiles/tier3_match.py [games_per_pairing] [sims] [threads] [--fake]   (--fake: CPU box, device replaced by the oracle-backed stub)"""
+usage: python tests/tools/tier3_match.py [games_per_pairing] [sims] [threads] [--fake]   (--fake: CPU box, device replaced by the oracle-backed stub)"""
 import json, os, subprocess, sys, math
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 L = os.path.join(ROOT, "game-ai_b200", "host", "GameLauncher")
 XML = os.path.join(ROOT, "tests", "golden", "run_config_tier3.xml")
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
